@@ -1,0 +1,677 @@
+// api.cu — the C-ABI of include/fluxb200.h: context, scene flattening to SoA
+// device buffers, sample-set upload / generation, render and trace entry points.
+//
+// Host-side counterpart of LocalWorker's loop body (fluxcore/src/workers.rs:46-64):
+// flux_set_scene = Scene::from_data + CameraBasis::new + Camera::new (minus the
+// samples), flux_set_samples / flux_generate_samples = MasterSampleSets::new,
+// flux_render_rows = Camera::render.
+#include "../../include/fluxb200.h"
+#include "flux_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = std::max<size_t>(n, 1);
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct flux_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    bool have_scene = false, have_samples = false, have_index = false;
+    flux_job_config cfg{};
+    DevCamera cam{};
+    DevScene scene{};
+    DevSamples ss{};
+    int accel_mode = 0;
+    bool count = false;
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+
+    DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink;
+    DevBuf<uint32_t> sph_meta, pln_meta, tri_meta, set_index, rows;
+    DevBuf<int32_t> ray_hit;
+    DevBuf<DevMaterial> materials;
+    DevBuf<double2> pixel, disc;
+    DevBuf<unsigned long long> counters;
+    DevBuf<unsigned int> work_counter;
+};
+
+namespace {
+
+int fail(flux_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ctx, FLUX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// CameraBasis::new, fluxcore/src/scene.rs:29-34 (host, f64, same op order)
+void camera_basis(V3 eye, V3 look_at, V3 up, V3 &u, V3 &v, V3 &w) {
+    w = normalize3(eye - look_at);
+    u = normalize3(cross3(up, w));
+    v = cross3(w, u);
+}
+
+V3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
+
+}  // namespace
+
+extern "C" {
+
+const char *flux_version(void) { return "fluxb200 0.1.0 (sm_100a)"; }
+
+const char *flux_last_error(const flux_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int flux_ctx_create(int device, flux_ctx **out) {
+    if (!out) {
+        g_create_error = "flux_ctx_create: out is null";
+        return FLUX_ERR_INVALID;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("flux_ctx_create: no CUDA device (") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                         "); libfluxb200 has no CPU fallback";
+        return FLUX_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "flux_ctx_create: device " + std::to_string(device) + " out of range (" + std::to_string(n) + " devices)";
+        return FLUX_ERR_NO_DEVICE;
+    }
+    flux_ctx *ctx = new (std::nothrow) flux_ctx();
+    if (!ctx) {
+        g_create_error = "flux_ctx_create: out of memory";
+        return FLUX_ERR_INVALID;
+    }
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_create_error = std::string("flux_ctx_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return FLUX_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "flux_ctx_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; libfluxb200 is built for sm_100a only";
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return FLUX_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (ctx->counters.reserve(CN_COUNT) != cudaSuccess || ctx->work_counter.reserve(1) != cudaSuccess ||
+        ctx->sink.reserve(1) != cudaSuccess) {
+        g_create_error = "flux_ctx_create: cudaMalloc failed";
+        delete ctx;
+        return FLUX_ERR_CUDA;
+    }
+    cudaMemsetAsync(ctx->counters.p, 0, CN_COUNT * sizeof(unsigned long long), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return FLUX_OK;
+}
+
+int flux_ctx_destroy(flux_ctx *ctx) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    {
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->sph.release(); ctx->pln.release(); ctx->tri.release(); ctx->hemi.release(); ctx->out.release();
+        ctx->ray_o.release(); ctx->ray_d.release(); ctx->ray_t.release(); ctx->sink.release();
+        ctx->sph_meta.release(); ctx->pln_meta.release(); ctx->tri_meta.release(); ctx->set_index.release();
+        ctx->rows.release(); ctx->ray_hit.release(); ctx->materials.release(); ctx->pixel.release();
+        ctx->disc.release(); ctx->counters.release(); ctx->work_counter.release();
+        cudaEventDestroy(ctx->ev0);
+        cudaEventDestroy(ctx->ev1);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return FLUX_OK;
+}
+
+int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_config *cfg) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!s || !cfg) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: null scene or config");
+    if (s->image_width == 0 || s->image_height == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: empty image");
+    if (cfg->sample_root == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: sample_root must be >= 1");
+    if (cfg->max_trace_depth > FLUX_MAX_DEPTH_CAP)
+        return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: max_trace_depth exceeds " + std::to_string(FLUX_MAX_DEPTH_CAP));
+    if ((s->n_materials && !s->materials) || (s->n_spheres && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
+        (s->n_planes && (!s->plane_point || !s->plane_normal || !s->plane_shape_id || !s->plane_material)) ||
+        (s->n_triangles && (!s->tri_v0 || !s->tri_v1 || !s->tri_v2 || !s->tri_shape_id || !s->tri_material)))
+        return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: null array with non-zero count");
+    auto check_ids = [&](const uint32_t *ids, const uint32_t *mats, uint32_t n, const char *what) -> bool {
+        for (uint32_t i = 0; i < n; i++) {
+            if (mats[i] >= s->n_materials) {
+                ctx->err = std::string("flux_set_scene: ") + what + " material index out of range";
+                return false;
+            }
+            if (i && ids[i] <= ids[i - 1]) {
+                ctx->err = std::string("flux_set_scene: ") + what + " shape ids must be strictly increasing";
+                return false;
+            }
+        }
+        return true;
+    };
+    if (!check_ids(s->sphere_shape_id, s->sphere_material, s->n_spheres, "sphere") ||
+        !check_ids(s->plane_shape_id, s->plane_material, s->n_planes, "plane") ||
+        !check_ids(s->tri_shape_id, s->tri_material, s->n_triangles, "triangle"))
+        return FLUX_ERR_INVALID;
+    for (uint32_t i = 0; i < s->n_materials; i++)
+        if (s->materials[i].kind > FLUX_MAT_GLOSSY) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: unknown material kind");
+
+    DeviceGuard g(ctx->device);
+    ctx->have_scene = false;
+    // ---- materials: per-material constants (same IEEE products as the reference) ----
+    std::vector<DevMaterial> mats(s->n_materials);
+    for (uint32_t i = 0; i < s->n_materials; i++) {
+        const flux_material &m = s->materials[i];
+        DevMaterial d{};
+        d.kind = m.kind;
+        for (int k = 0; k < 3; k++) {
+            double ck = m.color[k] * m.k;                      // cd*kd | color*power | cr*kr | cs*ks
+            d.c[k] = (m.kind == FLUX_MAT_MATTE) ? ck * FLUX_INV_PI : ck;  // brdf.rs:29
+        }
+        d.exp = m.exp;
+        d.inv_e1 = 1.0 / (m.exp + 1.0);  // samplers/src/lib.rs:135
+        mats[i] = d;
+    }
+    // ---- spheres: SoA + bounding boxes as Sphere::new (shapes.rs:154-169) ----
+    const uint32_t ns = s->n_spheres, np = s->n_planes, nt = s->n_triangles;
+    std::vector<double> sph((size_t)SPH_FIELDS * ns);
+    std::vector<uint32_t> sph_meta((size_t)2 * ns);
+    for (uint32_t i = 0; i < ns; i++) {
+        const double *c = s->sphere_center + 3 * i;
+        const double r = s->sphere_radius[i];
+        sph[(size_t)SPH_CX * ns + i] = c[0];
+        sph[(size_t)SPH_CY * ns + i] = c[1];
+        sph[(size_t)SPH_CZ * ns + i] = c[2];
+        sph[(size_t)SPH_R * ns + i] = r;
+        sph[(size_t)SPH_RR * ns + i] = r * r;                       // shapes.rs:179
+        sph[(size_t)SPH_INV * ns + i] = s->sphere_invert[i] ? -1.0 : 1.0;  // shapes.rs:181
+        sph[(size_t)SPH_C0X * ns + i] = c[0] - r;
+        sph[(size_t)SPH_C0Y * ns + i] = c[1] - r;
+        sph[(size_t)SPH_C0Z * ns + i] = c[2] - r;
+        sph[(size_t)SPH_C1X * ns + i] = c[0] + r;
+        sph[(size_t)SPH_C1Y * ns + i] = c[1] + r;
+        sph[(size_t)SPH_C1Z * ns + i] = c[2] + r;
+        sph_meta[i] = s->sphere_shape_id[i];
+        sph_meta[ns + i] = s->sphere_material[i];
+    }
+    std::vector<double> pln((size_t)PLN_FIELDS * np);
+    std::vector<uint32_t> pln_meta((size_t)2 * np);
+    for (uint32_t i = 0; i < np; i++) {
+        for (int k = 0; k < 3; k++) {
+            pln[(size_t)(PLN_PX + k) * np + i] = s->plane_point[3 * i + k];
+            pln[(size_t)(PLN_NX + k) * np + i] = s->plane_normal[3 * i + k];
+        }
+        pln_meta[i] = s->plane_shape_id[i];
+        pln_meta[np + i] = s->plane_material[i];
+    }
+    std::vector<double> tri((size_t)TRI_FIELDS * nt);
+    std::vector<uint32_t> tri_meta((size_t)2 * nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        for (int k = 0; k < 3; k++) {
+            const double v0 = s->tri_v0[3 * (size_t)i + k];
+            tri[(size_t)(TRI_V0X + k) * nt + i] = v0;
+            tri[(size_t)(TRI_E1X + k) * nt + i] = s->tri_v1[3 * (size_t)i + k] - v0;
+            tri[(size_t)(TRI_E2X + k) * nt + i] = s->tri_v2[3 * (size_t)i + k] - v0;
+        }
+        tri_meta[i] = s->tri_shape_id[i];
+        tri_meta[nt + i] = s->tri_material[i];
+    }
+    CK(ctx->materials.reserve(mats.size()));
+    CK(ctx->sph.reserve(sph.size()));
+    CK(ctx->sph_meta.reserve(sph_meta.size()));
+    CK(ctx->pln.reserve(pln.size()));
+    CK(ctx->pln_meta.reserve(pln_meta.size()));
+    CK(ctx->tri.reserve(tri.size()));
+    CK(ctx->tri_meta.reserve(tri_meta.size()));
+    auto up = [&](void *dst, const void *src, size_t bytes) {
+        return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+    };
+    CK(up(ctx->materials.p, mats.data(), mats.size() * sizeof(DevMaterial)));
+    CK(up(ctx->sph.p, sph.data(), sph.size() * sizeof(double)));
+    CK(up(ctx->sph_meta.p, sph_meta.data(), sph_meta.size() * sizeof(uint32_t)));
+    CK(up(ctx->pln.p, pln.data(), pln.size() * sizeof(double)));
+    CK(up(ctx->pln_meta.p, pln_meta.data(), pln_meta.size() * sizeof(uint32_t)));
+    CK(up(ctx->tri.p, tri.data(), tri.size() * sizeof(double)));
+    CK(up(ctx->tri_meta.p, tri_meta.data(), tri_meta.size() * sizeof(uint32_t)));
+    CK(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+
+    DevScene &sc = ctx->scene;
+    sc = DevScene{};
+    sc.n_spheres = ns;
+    sc.n_planes = np;
+    sc.n_tris = nt;
+    sc.n_materials = s->n_materials;
+    sc.sph = ctx->sph.p;
+    sc.sph_meta = ctx->sph_meta.p;
+    sc.pln = ctx->pln.p;
+    sc.pln_meta = ctx->pln_meta.p;
+    sc.tri = ctx->tri.p;
+    sc.tri_meta = ctx->tri_meta.p;
+    sc.materials = ctx->materials.p;
+
+    // ---- camera: CameraBasis::new (scene.rs:29-34) + render() prologue (trace.rs:54-60) ----
+    DevCamera &cam = ctx->cam;
+    cam = DevCamera{};
+    cam.eye = ld3(s->eye);
+    camera_basis(cam.eye, ld3(s->look_at), ld3(s->up), cam.u, cam.v, cam.w);
+    cam.aps = s->pixel_size / s->zoom_factor;
+    cam.half_w = (double)s->image_width * 0.5;
+    cam.half_h = (double)s->image_height * 0.5;
+    cam.factor = s->focal_distance / s->view_plane_distance;
+    cam.focal = s->focal_distance;
+    cam.lens_radius = s->lens_radius;
+    cam.focal_w = s->focal_distance * cam.w;
+    for (int k = 0; k < 3; k++) cam.bg[k] = s->background[k];
+    cam.W = s->image_width;
+    cam.H = s->image_height;
+    cam.max_depth = cfg->max_trace_depth;
+    ctx->cfg = *cfg;
+    ctx->have_scene = true;
+    // samples / set index belong to a job: a new scene invalidates them if shapes changed
+    if (ctx->have_samples && (ctx->ss.root != cfg->sample_root || ctx->ss.max_depth != cfg->max_trace_depth))
+        ctx->have_samples = false;
+    if (ctx->have_index && ctx->set_index.cap < (size_t)cam.W * cam.H) ctx->have_index = false;
+    return FLUX_OK;
+}
+
+static int alloc_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t num_sets) {
+    const size_t n = (size_t)root * root;
+    CK(ctx->pixel.reserve(n * num_sets));
+    CK(ctx->disc.reserve(n * num_sets));
+    CK(ctx->hemi.reserve(n * num_sets * max_depth * 3));
+    ctx->ss.root = root;
+    ctx->ss.n = (uint32_t)n;
+    ctx->ss.max_depth = max_depth;
+    ctx->ss.num_sets = num_sets;
+    ctx->ss.pixel = ctx->pixel.p;
+    ctx->ss.disc = ctx->disc.p;
+    ctx->ss.hemi = ctx->hemi.p;
+    return FLUX_OK;
+}
+
+int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t num_sets, const double *pixel_xy,
+                     const double *disc_xy, const double *hemi_xyz) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_set_samples: call flux_set_scene first");
+    if (root == 0 || num_sets == 0 || !pixel_xy || !disc_xy || (max_depth && !hemi_xyz))
+        return fail(ctx, FLUX_ERR_INVALID, "flux_set_samples: bad arguments");
+    if (root != ctx->cfg.sample_root || max_depth != ctx->cfg.max_trace_depth)
+        return fail(ctx, FLUX_ERR_INVALID, "flux_set_samples: root/max_depth differ from the job configuration");
+    if ((uint64_t)root * root > 0xFFFFFFFFull) return fail(ctx, FLUX_ERR_INVALID, "flux_set_samples: root too large");
+    DeviceGuard g(ctx->device);
+    ctx->have_samples = false;
+    int rc = alloc_samples(ctx, root, max_depth, num_sets);
+    if (rc) return rc;
+    const size_t n = (size_t)root * root;
+    CK(cudaMemcpyAsync(ctx->pixel.p, pixel_xy, n * num_sets * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->disc.p, disc_xy, n * num_sets * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (max_depth) CK(cudaMemcpyAsync(ctx->hemi.p, hemi_xyz, n * num_sets * max_depth * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_samples = true;
+    return FLUX_OK;
+}
+
+int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_generate_samples: call flux_set_scene first");
+    if (num_sets == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_generate_samples: num_sets must be >= 1");
+    const uint32_t root = ctx->cfg.sample_root, depth = ctx->cfg.max_trace_depth;
+    if ((size_t)4 * root * root > 200 * 1024)
+        return fail(ctx, FLUX_ERR_INVALID, "flux_generate_samples: sample_root too large for on-device permutations (use flux_set_samples)");
+    if ((size_t)num_sets * 4 > 200 * 1024)
+        return fail(ctx, FLUX_ERR_INVALID, "flux_generate_samples: num_sets too large (use flux_set_set_index)");
+    DeviceGuard g(ctx->device);
+    ctx->have_samples = false;
+    ctx->have_index = false;
+    int rc = alloc_samples(ctx, root, depth, num_sets);
+    if (rc) return rc;
+    CK(ctx->set_index.reserve((size_t)ctx->cam.W * ctx->cam.H));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    launch_generate_samples(seed, root, depth, num_sets, ctx->pixel.p, ctx->disc.p, ctx->hemi.p, ctx->stream);
+    launch_generate_set_index(seed, ctx->cam.H, ctx->cam.W, num_sets, ctx->set_index.p, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->have_samples = true;
+    ctx->have_index = true;
+    return FLUX_OK;
+}
+
+int flux_get_samples(flux_ctx *ctx, double *pixel_xy, double *disc_xy, double *hemi_xyz) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "flux_get_samples: no samples on the device");
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)ctx->ss.n * ctx->ss.num_sets;
+    if (pixel_xy) CK(cudaMemcpyAsync(pixel_xy, ctx->pixel.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (disc_xy) CK(cudaMemcpyAsync(disc_xy, ctx->disc.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hemi_xyz && ctx->ss.max_depth)
+        CK(cudaMemcpyAsync(hemi_xyz, ctx->hemi.p, n * ctx->ss.max_depth * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FLUX_OK;
+}
+
+int flux_get_set_index(flux_ctx *ctx, uint32_t *idx) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "flux_get_set_index: no set-index map on the device");
+    if (!idx) return fail(ctx, FLUX_ERR_INVALID, "flux_get_set_index: null output");
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(idx, ctx->set_index.p, (size_t)ctx->cam.W * ctx->cam.H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FLUX_OK;
+}
+
+int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_set_set_index: call flux_set_scene first");
+    if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "flux_set_set_index: set or generate samples first");
+    if (!idx) return fail(ctx, FLUX_ERR_INVALID, "flux_set_set_index: null map");
+    const size_t n = (size_t)ctx->cam.W * ctx->cam.H;
+    for (size_t i = 0; i < n; i++)
+        if (idx[i] >= ctx->ss.num_sets) return fail(ctx, FLUX_ERR_INVALID, "flux_set_set_index: set index out of range");
+    DeviceGuard g(ctx->device);
+    ctx->have_index = false;
+    CK(ctx->set_index.reserve(n));
+    CK(cudaMemcpyAsync(ctx->set_index.p, idx, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_index = true;
+    return FLUX_OK;
+}
+
+int flux_shard_rows(uint32_t image_height, uint32_t tile_rows, uint32_t rank, uint32_t world, uint32_t *rows,
+                    uint32_t *n_rows) {
+    if (!n_rows || tile_rows == 0 || world == 0 || rank >= world) return FLUX_ERR_INVALID;
+    uint32_t k = 0;
+    for (uint32_t r = 0; r < image_height; r++)
+        if ((r / tile_rows) % world == rank) {
+            if (rows) rows[k] = r;
+            k++;
+        }
+    *n_rows = k;
+    return FLUX_OK;
+}
+
+static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *d_out, cudaStream_t user_stream,
+                         bool sync_to_user) {
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "render: scene not set");
+    if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
+    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set");
+    if (n_rows == 0) return FLUX_OK;
+    if (!rows || !d_out) return fail(ctx, FLUX_ERR_INVALID, "render: null rows or output");
+    for (uint32_t k = 0; k < n_rows; k++) {
+        if (rows[k] >= ctx->cam.H) return fail(ctx, FLUX_ERR_INVALID, "render: row out of range");
+        if (k && rows[k] <= rows[k - 1]) return fail(ctx, FLUX_ERR_INVALID, "render: rows must be strictly ascending");
+    }
+    if ((uint64_t)n_rows * ctx->cam.W > 0xFFFFFFFFull) return fail(ctx, FLUX_ERR_INVALID, "render: too many pixels in one call");
+    cudaStream_t st = ctx->stream;
+    CK(ctx->rows.reserve(n_rows));
+    if (sync_to_user) {
+        // order after work already queued on the caller's stream
+        CK(cudaEventRecord(ctx->ev1, user_stream));
+        CK(cudaStreamWaitEvent(st, ctx->ev1, 0));
+    }
+    CK(cudaMemcpyAsync(ctx->rows.p, rows, (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->work_counter.p, 0, sizeof(unsigned int), st));
+    RenderParams p{};
+    p.scene = ctx->scene;
+    p.cam = ctx->cam;
+    p.ss = ctx->ss;
+    p.set_index = ctx->set_index.p;
+    p.rows = ctx->rows.p;
+    p.n_rows = n_rows;
+    p.out = d_out;
+    p.counters = ctx->counters.p;
+    p.work_counter = ctx->work_counter.p;
+    CK(cudaEventRecord(ctx->ev0, st));
+    launch_render(p, ctx->count, ctx->sm_count, st);
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaGetLastError());
+    if (sync_to_user) CK(cudaStreamWaitEvent(user_stream, ctx->ev1, 0));
+    return FLUX_OK;
+}
+
+int flux_render_row_list_device(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *d_out_rgb, void *cuda_stream) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    // rows are copied from pageable host memory: the copy is staged before return
+    return render_common(ctx, rows, n_rows, d_out_rgb, (cudaStream_t)cuda_stream, true);
+}
+
+int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *out_rgb) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (n_rows && !out_rgb) return fail(ctx, FLUX_ERR_INVALID, "render: null output");
+    DeviceGuard g(ctx->device);
+    const size_t elems = (size_t)n_rows * ctx->cam.W * 3;
+    CK(ctx->out.reserve(elems));
+    int rc = render_common(ctx, rows, n_rows, ctx->out.p, nullptr, false);
+    if (rc) return rc;
+    if (elems) CK(cudaMemcpyAsync(out_rgb, ctx->out.p, elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_rows) CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return FLUX_OK;
+}
+
+static int row_range(flux_ctx *ctx, uint32_t a, uint32_t b, std::vector<uint32_t> &rows) {
+    if (b < a) return fail(ctx, FLUX_ERR_INVALID, "render: row_end < row_start");
+    if (ctx->have_scene && b >= ctx->cam.H) return fail(ctx, FLUX_ERR_INVALID, "render: row out of range");
+    rows.resize((size_t)b - a + 1);
+    for (uint32_t r = a; r <= b; r++) rows[r - a] = r;
+    return FLUX_OK;
+}
+
+int flux_render_rows(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *out_rgb) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    std::vector<uint32_t> rows;
+    int rc = row_range(ctx, row_start, row_end_inclusive, rows);
+    if (rc) return rc;
+    return flux_render_row_list(ctx, rows.data(), (uint32_t)rows.size(), out_rgb);
+}
+
+int flux_render_rows_device(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *d_out_rgb, void *cuda_stream) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    std::vector<uint32_t> rows;
+    int rc = row_range(ctx, row_start, row_end_inclusive, rows);
+    if (rc) return rc;
+    return flux_render_row_list_device(ctx, rows.data(), (uint32_t)rows.size(), d_out_rgb, cuda_stream);
+}
+
+int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const double *d_d, int32_t *d_hit, double *d_t,
+                           void *cuda_stream) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_trace_rays: scene not set");
+    if (n == 0) return FLUX_OK;
+    if (!d_o || !d_d || !d_hit || !d_t) return fail(ctx, FLUX_ERR_INVALID, "flux_trace_rays: null pointer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t us = (cudaStream_t)cuda_stream;
+    CK(cudaEventRecord(ctx->ev1, us));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamWaitEvent(us, ctx->ev1, 0));
+    return FLUX_OK;
+}
+
+int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d, int32_t *hit, double *t) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_trace_rays: scene not set");
+    if (n == 0) return FLUX_OK;
+    if (!o || !d || !hit || !t) return fail(ctx, FLUX_ERR_INVALID, "flux_trace_rays: null pointer");
+    DeviceGuard g(ctx->device);
+    const uint64_t chunk = 1ull << 24;  // 16 Mi rays per launch bounds device memory at ~1 GB
+    const uint64_t m = std::min(n, chunk);
+    CK(ctx->ray_o.reserve(3 * m));
+    CK(ctx->ray_d.reserve(3 * m));
+    CK(ctx->ray_t.reserve(m));
+    CK(ctx->ray_hit.reserve(m));
+    float total_ms = 0.f;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t c = std::min(chunk, n - off);
+        CK(cudaMemcpyAsync(ctx->ray_o.p, o + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ray_d.p, d + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        launch_trace_rays(ctx->scene, c, ctx->ray_o.p, ctx->ray_d.p, ctx->ray_hit.p, ctx->ray_t.p, ctx->sm_count, ctx->stream);
+        ctx->launches += 1;
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hit + off, ctx->ray_hit.p, 4 * c, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(t + off, ctx->ray_t.p, 8 * c, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        total_ms += ms;
+    }
+    ctx->last_ms = total_ms;
+    return FLUX_OK;
+}
+
+int flux_enable_counters(flux_ctx *ctx, int enable) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    ctx->count = enable != 0;
+    return FLUX_OK;
+}
+
+int flux_get_counters(flux_ctx *ctx, flux_counters *out) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!out) return fail(ctx, FLUX_ERR_INVALID, "flux_get_counters: null output");
+    static_assert(sizeof(flux_counters) == CN_COUNT * sizeof(uint64_t), "flux_counters layout");
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(out, ctx->counters.p, sizeof(flux_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FLUX_OK;
+}
+
+int flux_reset_counters(flux_ctx *ctx) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(flux_counters), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FLUX_OK;
+}
+
+int flux_last_kernel_ms(flux_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return FLUX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    // device-pointer calls do not synchronise: resolve the events lazily here
+    if (cudaEventQuery(ctx->ev1) == cudaSuccess) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = v;
+    }
+    cudaGetLastError();
+    *ms = ctx->last_ms;
+    return FLUX_OK;
+}
+
+int flux_launch_count(flux_ctx *ctx, uint64_t *n) {
+    if (!ctx || !n) return FLUX_ERR_INVALID;
+    *n = ctx->launches;
+    return FLUX_OK;
+}
+
+int flux_set_accel_mode(flux_ctx *ctx, int mode) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(ctx, FLUX_ERR_INVALID, "flux_set_accel_mode: mode must be 0, 1 or 2");
+    ctx->accel_mode = mode;
+    return FLUX_OK;
+}
+
+int flux_measure_fp64_peak(flux_ctx *ctx, double *ginstr_per_s) {
+    if (!ctx || !ginstr_per_s) return FLUX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    double best = 0.0;
+    launch_fp64_peak(ctx->sm_count, 2000, ctx->sink.p, ctx->stream);  // warm-up
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        double instr = launch_fp64_peak(ctx->sm_count, 20000, ctx->sink.p, ctx->stream);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->launches += 1;
+        if (ms > 0.f) best = std::max(best, instr / (ms * 1e-3) / 1e9);
+    }
+    ctx->launches += 1;
+    *ginstr_per_s = best;
+    return FLUX_OK;
+}
+
+// Image::write, fluxcore/src/image.rs:42-60: "P3\n{W} {H}\n65535\n" then one
+// "r g b" line per pixel, (c * 65535.99) as u16 (saturating, NaN -> 0).
+int flux_write_ppm(const char *path, uint32_t width, uint32_t height, const double *rgb) {
+    if (!path || !rgb) return FLUX_ERR_INVALID;
+    FILE *f = fopen(path, "w");
+    if (!f) return FLUX_ERR_INVALID;
+    auto q = [](double c) -> unsigned {
+        double v = c * 65535.99;
+        if (!(v == v) || v <= 0.0) return 0u;
+        if (v >= 65535.0) return 65535u;
+        return (unsigned)v;
+    };
+    fprintf(f, "P3\n%u %u\n65535\n", width, height);
+    const size_t n = (size_t)width * height;
+    for (size_t i = 0; i < n; i++) fprintf(f, "%u %u %u\n", q(rgb[3 * i]), q(rgb[3 * i + 1]), q(rgb[3 * i + 2]));
+    return fclose(f) == 0 ? FLUX_OK : FLUX_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// flux_kernels.cuh — kernel entry points shared between translation units.
+#pragma once
+#include "flux_scene.cuh"
+
+#define FLUX_MAX_DEPTH_CAP 32  // per-path (f, weight) stack entries
+
+// Camera::render for a list of rows (trace.rs:53-97).
+void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
+
+// Scene::hit on an explicit ray batch (scene.rs:156-160).
+void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
+                       int sm_count, cudaStream_t stream);
+
+// MasterSampleSets::new on the device (sampling.rs:13-33) + per-row set-index permutations (sampling.rs:35-40).
+void launch_generate_samples(uint64_t seed, uint32_t root, uint32_t max_depth, uint32_t num_sets, double2 *pixel,
+                             double2 *disc, double *hemi, cudaStream_t stream);
+void launch_generate_set_index(uint64_t seed, uint32_t H, uint32_t W, uint32_t num_sets, uint32_t *idx,
+                               cudaStream_t stream);
+
+// FP64 issue-rate microbenchmark; returns total FP64 instructions executed.
+double launch_fp64_peak(int sm_count, int iters, double *sink, cudaStream_t stream);

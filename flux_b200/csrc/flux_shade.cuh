@@ -1,0 +1,67 @@
+// flux_shade.cuh — BRDF sampling with the reference's operation order.
+//
+//   Lambertian::sample_f       fluxcore/src/brdf.rs:20-30
+//   PerfectSpecular::sample_f  fluxcore/src/brdf.rs:39-45
+//   GlossySpecular::sample_f   fluxcore/src/brdf.rs:55-78
+//   to_unit_hemi               samplers/src/lib.rs:133-142
+//
+// Each returns the child direction wi and the weight the material applies to
+// the child's radiance: result = (f (*) L_child) * (n.wi / pdf)
+// (materials.rs:31-32, 69-70).  f is returned by reference.
+#pragma once
+#include "flux_scene.cuh"
+
+// Matte: materials.rs:19-33 + brdf.rs:20-30.  f is the per-material constant
+// (cd*kd)*INV_PI precomputed on the host (same IEEE products).
+__device__ __forceinline__ void matte_sample(V3 normal, V3 hemi, V3 &wi, double &weight) {
+    V3 w = normal;
+    V3 v = normalize3(cross3(mk3(0.0034, 1.0, 0.0071), w));
+    V3 u = cross3(v, w);
+    wi = normalize3((hemi.x * u + hemi.y * v) + hemi.z * w);
+    double pdf = dot3(normal, wi) * FLUX_INV_PI;
+    double ndotwi = dot3(normal, wi);
+    weight = ndotwi / pdf;
+}
+
+// Reflective + PerfectSpecular: materials.rs:57-71 + brdf.rs:39-45.
+__device__ __forceinline__ void specular_sample(V3 normal, V3 dir, V3 &wi, double &weight) {
+    V3 wo = dir * -1.0;
+    double ndotwo = dot3(normal, wo);
+    wi = neg3(wo) + normal * ndotwo * 2.0;
+    double pdf = dot3(normal, wi);
+    weight = dot3(normal, wi) / pdf;
+}
+
+// samplers/src/lib.rs:133-142 with inv_e1 = 1.0/(e+1.0) precomputed.
+__device__ __forceinline__ V3 to_unit_hemi_dev(double px, double py, double inv_e1) {
+    double sin_phi, cos_phi;
+    sincos((2.0 * FLUX_PI) * px, &sin_phi, &cos_phi);
+    double cos_theta = pow(1.0 - py, inv_e1);
+    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+    double pu = sin_theta * cos_phi;
+    double pv = sin_theta * sin_phi;
+    double pw = cos_theta;
+    return normalize3(mk3(pu, pv, pw));
+}
+
+// Reflective + GlossySpecular: materials.rs:57-71 + brdf.rs:55-78.
+// lobe multiplies the per-material constant cs*ks to give f.
+__device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, double sqy, double ex, double inv_e1,
+                                              V3 &wi, double &weight, double &lobe, bool &flipped) {
+    V3 wo = dir * -1.0;
+    double ndotwo = dot3(normal, wo);
+    V3 r = neg3(wo) + normal * ndotwo * 2.0;
+    V3 w = r;
+    V3 u = normalize3(cross3(mk3(0.00424, 1.0, 0.00764), w));
+    V3 v = cross3(u, w);
+    V3 hs = to_unit_hemi_dev(sqx, sqy, inv_e1);
+    V3 wi0 = (u * hs.x + v * hs.y) + w * hs.z;
+    flipped = dot3(normal, wi0) < 0.0;
+    if (flipped)
+        wi = (u * -hs.x - v * hs.y) + w * hs.z;
+    else
+        wi = wi0;
+    lobe = pow(dot3(r, wi), ex);
+    double pdf = lobe * dot3(normal, wi);
+    weight = dot3(normal, wi) / pdf;
+}

@@ -1,0 +1,223 @@
+// render.cu — the per-pixel render loop on sm_100a.
+//
+// Camera::render (fluxcore/src/trace.rs:53-97) → Scene::shade (scene.rs:162-172)
+// → Material::path_shade (materials.rs:19-71), iterated instead of recursed:
+// each material spawns exactly one child ray, so a path is a chain; the
+// (f, weight) pair of every bounce is kept on a per-path stack and radiance is
+// combined innermost-first exactly as the recursion returns it
+// (SURVEY.md H4):  L_k = (f_k (*) L_{k+1}) * w_k.
+//
+// Work decomposition: a group of G = min(32, pow2ceil(spp)) lanes owns one
+// pixel; lane g takes samples g, g+G, ...; the per-pixel sum is a fixed-shape
+// xor-shuffle tree, so the result does not depend on grid size, scheduling or
+// the number of GPUs.
+#include "flux_intersect.cuh"
+#include "flux_kernels.cuh"
+#include "flux_shade.cuh"
+
+struct Rgb {
+    double r, g, b;
+};
+
+// Body of the per-sample loop, trace.rs:71-80.
+__device__ __forceinline__ void primary_ray(const DevCamera &cam, uint32_t row, uint32_t col, double2 ps, double2 ds,
+                                            V3 &o, V3 &d) {
+    double u = cam.aps * (((double)col - cam.half_w) + ps.x);
+    double v = cam.aps * (((double)(cam.H - row) - cam.half_h) + ps.y);
+    double lpx = ds.x * cam.lens_radius;
+    double lpy = ds.y * cam.lens_radius;
+    double px2 = u * cam.factor;
+    double py2 = v * cam.factor;
+    d = normalize3(((px2 - lpx) * cam.u + (py2 - lpy) * cam.v) - cam.focal_w);
+    o = (cam.eye + lpx * cam.u) + lpy * cam.v;
+}
+
+// scene.shade(&r, 1, ..) for one camera sample.
+template <bool COUNT>
+__device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uint32_t set, uint32_t i, double2 ps,
+                                          unsigned long long *cn) {
+    double sf[FLUX_MAX_DEPTH_CAP][4];  // (f.r, f.g, f.b, weight) per bounce
+    uint32_t top = 0;
+    Rgb L;
+    uint32_t depth = 1;
+    const DevScene &sc = p.scene;
+    for (;;) {
+        if (depth > p.cam.max_depth) {  // scene.rs:164-165
+            if (COUNT) cn[CN_DEPTH_CUT]++;
+            L = Rgb{0.0, 0.0, 0.0};
+            break;
+        }
+        if (COUNT) cn[CN_SEGMENTS]++;
+        RayCtx r = make_ray(o, d);
+        HitRef h = closest_hit_linear<COUNT>(sc, r, cn);
+        if (h.shape_id == 0xFFFFFFFFu) {  // scene.rs:168
+            if (COUNT) cn[CN_MISS]++;
+            L = Rgb{p.cam.bg[0], p.cam.bg[1], p.cam.bg[2]};
+            break;
+        }
+        if (COUNT) cn[h.kind == KIND_SPHERE ? CN_HIT_SPHERE : (h.kind == KIND_PLANE ? CN_HIT_PLANE : CN_HIT_TRI)]++;
+        HitRec hr = build_hit(sc, r, h);
+        const DevMaterial *m = sc.materials + hr.material;
+        uint32_t kind = m->kind;
+        double c0 = m->c[0], c1 = m->c[1], c2 = m->c[2];
+        if (kind == FLUX_MAT_EMISSIVE) {  // materials.rs:42-49
+            if (COUNT) cn[CN_EMISSIVE]++;
+            if (dot3(hr.normal * -1.0, d) > 0.0)
+                L = Rgb{c0, c1, c2};
+            else
+                L = Rgb{0.0, 0.0, 0.0};
+            break;
+        }
+        V3 wi;
+        double weight;
+        if (kind == FLUX_MAT_MATTE) {  // materials.rs:19-33
+            if (COUNT) cn[CN_MATTE]++;
+            const double *hp = p.ss.hemi + (((size_t)set * p.ss.max_depth + (depth - 1)) * p.ss.n + i) * 3;
+            matte_sample(hr.normal, mk3(hp[0], hp[1], hp[2]), wi, weight);
+        } else if (kind == FLUX_MAT_REFLECTIVE) {  // materials.rs:57-71, brdf.rs:39-45
+            if (COUNT) cn[CN_SPECULAR]++;
+            specular_sample(hr.normal, d, wi, weight);
+        } else {  // glossy: materials.rs:57-71, brdf.rs:55-78
+            if (COUNT) cn[CN_GLOSSY]++;
+            double lobe;
+            bool flipped;
+            glossy_sample(hr.normal, d, ps.x, ps.y, m->exp, m->inv_e1, wi, weight, lobe, flipped);
+            if (COUNT && flipped) cn[CN_GLOSSY_FLIP]++;
+            c0 *= lobe;
+            c1 *= lobe;
+            c2 *= lobe;
+        }
+        sf[top][0] = c0;
+        sf[top][1] = c1;
+        sf[top][2] = c2;
+        sf[top][3] = weight;
+        top++;
+        o = hr.point;
+        d = wi;
+        depth++;
+    }
+    while (top > 0) {  // unwind: (f (*) L) * w, materials.rs:31-32,69-70
+        top--;
+        L.r = (sf[top][0] * L.r) * sf[top][3];
+        L.g = (sf[top][1] * L.g) * sf[top][3];
+        L.b = (sf[top][2] * L.b) * sf[top][3];
+    }
+    return L;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ RenderParams p, uint32_t G) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ppw = 32u / G;  // pixels per warp
+    const uint32_t g = lane % G;
+    const uint32_t W = p.cam.W;
+    const uint32_t npix = p.n_rows * W;
+    const uint32_t n_items = (npix + ppw - 1) / ppw;
+    const uint32_t n = p.ss.n;
+    unsigned long long cn[COUNT ? CN_COUNT : 1];
+    if (COUNT)
+        for (int k = 0; k < CN_COUNT; k++) cn[k] = 0;
+    const double pixel_denom = 1.0 / (double)((unsigned long long)p.ss.root * p.ss.root);  // trace.rs:59
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const uint32_t pixel = item * ppw + lane / G;
+        const bool valid = pixel < npix;
+        Rgb acc = Rgb{0.0, 0.0, 0.0};
+        uint32_t row = 0, col = 0;
+        if (valid) {
+            const uint32_t rk = pixel / W;
+            col = pixel - rk * W;
+            row = p.rows[rk];
+            const uint32_t set = p.set_index[(size_t)row * W + col];
+            const double2 *ps = p.ss.pixel + (size_t)set * n;
+            const double2 *ds = p.ss.disc + (size_t)set * n;
+            for (uint32_t i = g; i < n; i += G) {
+                double2 s = ps[i];
+                double2 l = ds[i];
+                V3 o, d;
+                primary_ray(p.cam, row, col, s, l, o, d);
+                if (COUNT) cn[CN_SAMPLES]++;
+                Rgb c = trace_path<COUNT>(p, o, d, set, i, s, cn);
+                acc.r += c.r;
+                acc.g += c.g;
+                acc.b += c.b;
+            }
+        }
+        for (uint32_t off = G >> 1; off > 0; off >>= 1) {
+            acc.r += __shfl_xor_sync(0xffffffffu, acc.r, off);
+            acc.g += __shfl_xor_sync(0xffffffffu, acc.g, off);
+            acc.b += __shfl_xor_sync(0xffffffffu, acc.b, off);
+        }
+        if (valid && g == 0) {  // trace.rs:85-86, color.rs:35-44
+            double r = acc.r * pixel_denom, gg = acc.g * pixel_denom, b = acc.b * pixel_denom;
+            double mx1 = r > gg ? r : gg;
+            double mx2 = mx1 > b ? mx1 : b;
+            if (mx2 > 1.0) {
+                double inv = 1.0 / mx2;
+                r *= inv;
+                gg *= inv;
+                b *= inv;
+            }
+            double *o = p.out + (size_t)pixel * 3;
+            o[0] = r;
+            o[1] = gg;
+            o[2] = b;
+        }
+    }
+    if (COUNT) {
+        for (int k = 0; k < CN_COUNT; k++)
+            if (cn[k]) atomicAdd(p.counters + k, cn[k]);
+    }
+}
+
+static uint32_t group_width(uint32_t n) {
+    uint32_t G = 1;
+    while (G < n && G < 32) G <<= 1;
+    return G;
+}
+
+void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
+    const uint32_t G = group_width(p.ss.n);
+    const int threads = 256;
+    const uint32_t ppw = 32 / G;
+    const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;
+    const uint64_t n_items = (npix + ppw - 1) / ppw;
+    uint64_t want = (n_items + (threads / 32) - 1) / (threads / 32);
+    uint64_t cap = (uint64_t)sm_count * 4;
+    int blocks = (int)(want < cap ? (want ? want : 1) : cap);
+    if (count)
+        render_kernel<true><<<blocks, threads, 0, stream>>>(p, G);
+    else
+        render_kernel<false><<<blocks, threads, 0, stream>>>(p, G);
+}
+
+// ---- Scene::hit on an explicit ray batch (K6) -------------------------------
+__global__ void __launch_bounds__(256) trace_rays_kernel(const __grid_constant__ DevScene sc, uint64_t n,
+                                                         const double *__restrict__ o, const double *__restrict__ d,
+                                                         int32_t *__restrict__ hit, double *__restrict__ t) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        RayCtx r = make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+        HitRef h = closest_hit_linear<false>(sc, r, nullptr);
+        if (h.shape_id == 0xFFFFFFFFu) {
+            hit[i] = -1;
+            t[i] = __longlong_as_double(0x7FF0000000000000ll);
+        } else {
+            hit[i] = (int32_t)h.shape_id;
+            t[i] = h.t;
+        }
+    }
+}
+
+void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
+                       int sm_count, cudaStream_t stream) {
+    if (n == 0) return;
+    const int threads = 256;
+    uint64_t want = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count * 8;
+    int blocks = (int)(want < cap ? want : cap);
+    trace_rays_kernel<<<blocks, threads, 0, stream>>>(sc, n, o, d, hit, t);
+}
