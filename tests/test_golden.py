@@ -1,0 +1,59 @@
+"""Golden fixtures (CPU part): the oracle reproduces its committed regression vectors bit-for-bit and
+agrees statistically with the reference's own converged render of demo2 (demo.png, README.md:1-3)."""
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from flux_b200 import JobConfiguration
+from oracle import oracle_py as O
+from tests.golden import make_golden as G
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_oracle_regression_vectors(name):
+    want = np.load(os.path.join(HERE, name + ".npz"))
+    got = G.make(name)
+    assert np.array_equal(got["rows"], want["rows"])
+    assert np.array_equal(got["counters"], want["counters"])
+    if "deterministic" in name:
+        assert np.array_equal(got["image"].view(np.uint64), want["image"].view(np.uint64))
+    else:  # glossy paths call libm pow/sin/cos: allow a libm-version ulp, nothing more
+        assert np.allclose(got["image"], want["image"], rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_oracle_ray_fixture(demo2):
+    f = np.load(os.path.join(HERE, "oracle_rays_demo2.npz"))
+    hit, t = O.trace_rays(demo2.flatten(), f["origins"], f["dirs"])
+    assert np.array_equal(hit, f["hit"]) and np.array_equal(t.view(np.uint64), f["t"].view(np.uint64))
+
+
+def reference_image():
+    """demo.png: 800x600 8-bit, values are linear c*255."""
+    return np.asarray(Image.open(os.path.join(HERE, "demo2_reference.png")).convert("RGB"), dtype=np.float64) / 255.0
+
+
+def test_oracle_matches_reference_render_statistically(demo2):
+    """The only reference-produced artefact: demo2 at 16384 spp.  At 64 spp on every 4th row the oracle
+    (measured when this test was written) gives RMSE 0.0662, 1x16-block RMSE 0.0178 and channel means
+    within 0.4 %; thresholds carry ~25 % margin.  A wrong camera, material or light model fails by far
+    (a black or mirrored image gives block RMSE > 0.2)."""
+    ref = reference_image()
+    assert ref.shape == (600, 800, 3)
+    cfg = JobConfiguration(8, 5, 50)
+    ss = O.generate_samples(1, 8, 5, 800)
+    ss.set_index = O.generate_set_index(1, 600, 800, 800)
+    rows = np.arange(0, 600, 4)
+    img = O.render_row_list(demo2.flatten(), cfg, ss, rows)
+    r = ref[rows]
+    assert np.isfinite(img).all() and img.max() <= 1.0
+    rmse = np.sqrt(np.mean((img - r) ** 2))
+    bm = lambda a: a.reshape(a.shape[0], 50, 16, 3).mean(2)  # noqa: E731
+    block_rmse = np.sqrt(np.mean((bm(img) - bm(r)) ** 2))
+    ratio = img.reshape(-1, 3).mean(0) / r.reshape(-1, 3).mean(0)
+    assert rmse < 0.083, rmse
+    assert block_rmse < 0.0225, block_rmse
+    assert np.all(np.abs(ratio - 1.0) < 0.01), ratio

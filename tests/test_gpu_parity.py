@@ -205,3 +205,57 @@ def test_error_behaviour(gpu_ctx, demo1):
     with pytest.raises(FluxError):
         GpuContext(99)
     c.close()
+
+
+# ---- committed golden fixtures (tests/golden/*.npz, generated by tests/golden/make_golden.py) ----------
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name", ["oracle_demo1_64x48_r3", "oracle_demo2_rows_r2", "oracle_mixed_96x64_r4",
+                                  "oracle_deterministic_96x64_r2"])
+def test_gpu_matches_golden_fixture(gpu_ctx, name):
+    from tests.golden import make_golden as G
+    factory, root, depth, seed = G.CASES[name]
+    sd = factory()
+    W, H = sd.output_settings.image_width, sd.output_settings.image_height
+    cfg = JobConfiguration(root, depth, 50)
+    want = _golden(name)
+    ss = Hp.oracle_samples(seed, cfg, W, H)
+    Hp.upload(gpu_ctx, sd.flatten(), cfg, ss)
+    gpu_ctx.enable_counters(True)
+    gpu_ctx.reset_counters()
+    try:
+        img = gpu_ctx.render_row_list(want["rows"], W)
+        cn = gpu_ctx.counters()
+    finally:
+        gpu_ctx.enable_counters(False)
+    assert Hp.rel_err(img, want["image"]) <= (1e-13 if "deterministic" in name else RADIANCE_RTOL)
+    got = np.array([cn[k] for k in sorted(cn)], np.uint64)
+    assert np.array_equal(got, want["counters"]), dict(zip(sorted(cn), zip(got, want["counters"])))
+
+
+def test_gpu_matches_golden_rays(gpu_ctx, demo2):
+    f = _golden("oracle_rays_demo2")
+    gpu_ctx.set_scene(demo2.flatten(), JobConfiguration(1))
+    hit, t = gpu_ctx.trace_rays(f["origins"], f["dirs"])
+    assert np.array_equal(hit, f["hit"]) and np.array_equal(t.view(np.uint64), f["t"].view(np.uint64))
+
+
+def test_gpu_converged_demo2_matches_reference_png(gpu_ctx, demo2):
+    """Layer-2 parity (north_star): the converged image of the stochastic scene against the reference's
+    own render (demo.png = demo2 at 16384 spp, 8-bit).  4096 spp here; expected RMSE = sqrt(noise(4096)^2 +
+    noise_ref(16384)^2 + quantisation^2) ~ sqrt(0.0083^2 + 0.0041^2 + 0.0011^2) ~ 0.0093."""
+    from tests.test_golden import reference_image
+    ref = reference_image()
+    cfg = JobConfiguration(64, 5, 50)
+    gpu_ctx.set_scene(demo2.flatten(), cfg)
+    gpu_ctx.generate_samples(1, 800)
+    img = gpu_ctx.render_rows(0, 599, 800)
+    assert np.isfinite(img).all()
+    rmse = float(np.sqrt(np.mean((img - ref) ** 2)))
+    ratio = img.reshape(-1, 3).mean(0) / ref.reshape(-1, 3).mean(0)
+    print(f"demo2 @4096spp vs demo.png: rmse {rmse:.5f}, channel mean ratio {ratio}")
+    assert rmse < 0.015, rmse
+    assert np.all(np.abs(ratio - 1.0) < 0.005), ratio

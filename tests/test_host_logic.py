@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: scene YAML loading (the reference's scenes load unchanged),
+flattening, work units, sharding, the op model."""
+import os
+
+import numpy as np
+import pytest
+
+from flux_b200 import (Emissive, GlossyReflective, JobConfiguration, Matte, PlaneData, SceneData, SphereData,
+                       work_units)
+from flux_b200 import _capi
+from flux_b200.opsmodel import algorithmic_ops, ops_per_sample
+from flux_b200.worker import shard_rows
+
+
+def test_demo1_loads_unchanged(demo1):
+    assert demo1.scene_name == "demo1"
+    os_ = demo1.output_settings
+    assert (os_.image_width, os_.image_height, os_.pixel_size) == (800, 600, 0.5)
+    assert len(demo1.shapes) == 6  # 5 spheres + 1 plane; the commented-out area light is absent
+    assert isinstance(demo1.shapes[0], SphereData) and demo1.shapes[0].invert is True
+    assert isinstance(demo1.shapes[0].material, Emissive) and demo1.shapes[0].material.power == 1.0
+    assert isinstance(demo1.shapes[5], PlaneData) and demo1.shapes[5].normal == (0.0, 1.0, 0.0)
+    assert demo1.shapes[3].material == GlossyReflective(0.9, (0.9, 1.0, 0.9), 100000.0)
+    assert demo1.camera_settings.eye == (2.5, 1.5, -9.0) and demo1.camera_data.lens_radius == 0.0
+
+
+def test_demo2_anchors_aliases_and_unknown_keys(demo2):
+    # demo2.yml defines materials under ignored top-level keys mat1..3 and aliases them (demo2.yml:1-15,54)
+    assert len(demo2.shapes) == 13
+    mats = [s.material for s in demo2.shapes[2:12]]
+    assert mats[0] == GlossyReflective(0.5, (0.8, 0.6, 1.0), 10000.0)
+    assert mats[0] == mats[3] == mats[6] == mats[9]
+    assert mats[1] == GlossyReflective(0.5, (0.9, 1.0, 0.7), 100.0) and mats[2].reflect_exponent == 10.0
+    assert demo2.camera_data.lens_radius == 0.09
+    flat = demo2.flatten()
+    assert flat.struct.n_spheres == 12 and flat.struct.n_planes == 1 and flat.struct.n_materials == 6
+    assert list(np.ctypeslib.as_array(flat.struct.sphere_shape_id, (12,))) == list(range(12))
+    assert flat.struct.plane_shape_id[0] == 12
+
+
+def test_yaml_errors_mirror_serde():
+    base = open(os.path.join(os.path.dirname(__file__), "..", "scenes", "demo1.yml")).read()
+    with pytest.raises(ValueError, match="missing field `invert`"):
+        SceneData.from_yaml_string(base.replace("      invert: true\n", "", 1))
+    with pytest.raises(ValueError, match="unknown variant `Cube`"):
+        SceneData.from_yaml_string(base.replace("  - Plane:", "  - Cube:"))
+    with pytest.raises(ValueError, match="missing field `background`"):
+        SceneData.from_yaml_string(base.replace("background: [0, 0, 0]\n", ""))
+    with pytest.raises(ValueError, match="unknown variant `Shiny`"):
+        SceneData.from_yaml_string(base.replace("        Emissive:", "        Shiny:", 1))
+    with pytest.raises(ValueError, match="sequence of 3"):
+        SceneData.from_yaml_string(base.replace("eye: [2.5, 1.5, -9.0]", "eye: [2.5, 1.5]"))
+    sd = SceneData.from_yaml_string(base + "\nsome_unknown_key: 42\n")  # unknown keys are ignored
+    assert sd.scene_name == "demo1"
+
+
+def test_flatten_shape_ids_share_one_index_space():
+    m = Matte((1, 1, 1), (1, 1, 1), 1.0)
+    sd = SceneData.from_yaml_string(open(os.path.join(os.path.dirname(__file__), "..", "scenes", "demo1.yml")).read())
+    sd.shapes = [PlaneData((0, 0, 0), (0, 1, 0), m), SphereData((0, 1, 0), 1.0, m, False),
+                 PlaneData((0, 5, 0), (0, -1, 0), m), SphereData((3, 1, 0), 1.0, m, True)]
+    f = sd.flatten().struct
+    assert [f.plane_shape_id[i] for i in range(2)] == [0, 2]
+    assert [f.sphere_shape_id[i] for i in range(2)] == [1, 3]
+    assert [f.sphere_invert[i] for i in range(2)] == [0, 1]
+    assert f.n_materials == 1  # identical materials are shared
+
+
+def test_with_size_only_changes_resolution(demo1):
+    sd = demo1.with_size(512, 512)  # BASELINE config 1
+    assert (sd.output_settings.image_width, sd.output_settings.image_height) == (512, 512)
+    assert sd.shapes == demo1.shapes and sd.camera_data == demo1.camera_data
+
+
+def test_work_units_cover_all_rows():
+    us = work_units(600, 50)
+    assert len(us) == 12 and us[0].row_start == 0 and us[-1].row_end == 599
+    assert all(u.row_end - u.row_start == 49 for u in us)
+    us = work_units(601, 50)  # the reference drops this trailing row (job.rs:76 `i < h - 1`); we do not
+    assert us[-1].row_start == 600 and us[-1].row_end == 600
+    assert [(u.row_start, u.row_end) for u in work_units(1, 50)] == [(0, 0)]
+    with pytest.raises(ValueError):
+        work_units(10, 0)  # job.rs:67-70 panics
+
+
+@pytest.mark.parametrize("height,tile,world", [(600, 4, 1), (600, 4, 8), (601, 4, 8), (7, 4, 8), (512, 8, 3), (1080, 4, 8)])
+def test_shard_rows_partition(height, tile, world):
+    parts = [shard_rows(height, tile, r, world) for r in range(world)]
+    allr = np.sort(np.concatenate(parts))
+    assert np.array_equal(allr, np.arange(height))
+    for r, p in enumerate(parts):
+        assert np.all(np.diff(p) > 0) and np.all((p // tile) % world == r)
+    assert max(map(len, parts)) - min(map(len, parts)) <= tile
+
+
+def test_shard_rows_bad_arguments():
+    for args in [(10, 0, 0, 1), (10, 4, 1, 1), (10, 4, 0, 0)]:
+        with pytest.raises(ValueError):
+            shard_rows(*args)
+
+
+def test_ops_model_matches_survey_magnitude(demo2):
+    """demo2 needs ~920 algorithmic FP64 ops per sample (oracle counters x op table)."""
+    from oracle import oracle_py as O
+    cfg = JobConfiguration(2, 5, 50)
+    ss = O.generate_samples(1, 2, 5, 800)
+    ss.set_index = O.generate_set_index(1, 600, 800, 800)
+    rows = np.arange(0, 600, 20)
+    _, cn = O.render_row_list(demo2.flatten(), cfg, ss, rows, counters=True)
+    assert cn["samples"] == 30 * 800 * 4
+    assert 880 < ops_per_sample(cn) < 960
+    assert algorithmic_ops(cn) == pytest.approx(ops_per_sample(cn) * cn["samples"])
+    assert cn["segments"] == cn["emissive"] + cn["matte"] + cn["glossy"] + cn["specular"] + cn["miss"]
+    assert cn["hit_sphere"] + cn["hit_plane"] + cn["miss"] == cn["segments"]
+    assert set(_capi.COUNTER_FIELDS) == set(cn)
