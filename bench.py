@@ -170,7 +170,7 @@ def main():
     import torch
     from flux_b200 import JobConfiguration, SceneData
     from flux_b200.opsmodel import algorithmic_ops
-    from flux_b200.worker import GpuContext, shard_rows
+    from flux_b200.worker import GpuContext
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,25 +193,17 @@ def main():
     ctx = GpuContext(local_rank)
     ctx.set_scene(flat, cfg)
     ctx.generate_samples(SEED, W)
-    my_rows = shard_rows(H, TILE_ROWS, rank, world)
-    all_rows = [shard_rows(H, TILE_ROWS, r, world) for r in range(world)]
-    max_rows = max(len(r) for r in all_rows)
+    from flux_b200.sharding import FrameGather, FramePlan
+    plan = FramePlan(H, W, TILE_ROWS, world)
+    my_rows = plan.my_rows(rank)
     stream = torch.cuda.current_stream().cuda_stream
-    # per-rank packed slice, padded to max_rows so the gather is one equal-sized collective
-    mine = torch.zeros((max_rows, W, 3), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world, max_rows, W, 3), dtype=torch.float64, device=dev) if world > 1 else None
-    frame = torch.empty((H, W, 3), dtype=torch.float64, device=dev)
-    row_index = [torch.from_numpy(r.astype(np.int64)).to(dev) for r in all_rows]
+    fg = FrameGather(plan, rank, dev, dist)   # packed slice (padded), gathered slices, assembled frame
+    mine = fg.mine
     host_frame = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
 
     def step_resident():
         ctx.render_row_list_device(my_rows, mine.data_ptr(), stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, mine)
-            for r in range(world):
-                frame.index_copy_(0, row_index[r], gathered[r, :len(all_rows[r])])
-        else:
-            frame.index_copy_(0, row_index[0], mine[:len(my_rows)])
+        fg.gather()
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,9 +249,7 @@ def main():
         ctx.generate_samples(SEED, W)
         if world > 1:
             ctx.render_row_list_device(my_rows, mine.data_ptr(), stream)
-            dist.all_gather_into_tensor(gathered, mine)
-            for r in range(world):
-                frame.index_copy_(0, row_index[r], gathered[r, :len(all_rows[r])])
+            frame = fg.gather()
             if rank == 0:
                 host_frame.copy_(frame, non_blocking=False)
         else:
