@@ -85,11 +85,14 @@ PROTOTYPES = {
     "flux_last_kernel_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
     "flux_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
     "flux_set_accel_mode": (C.c_int, [_ctx, C.c_int]),
+    "flux_set_kernel_mode": (C.c_int, [_ctx, C.c_int]),
+    "flux_set_glossy_table": (C.c_int, [_ctx, C.c_int]),
     "flux_measure_fp64_peak": (C.c_int, [_ctx, _dp]),
     "flux_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _dp]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfluxb200.so")
+# FLUXB200_LIB selects an alternative build of the same library (A/B of compile-time kernel variants)
+LIB_PATH = os.environ.get("FLUXB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfluxb200.so")
 _lib = None
 
 

@@ -54,11 +54,14 @@ struct flux_ctx {
     DevScene scene{};
     DevSamples ss{};
     int accel_mode = 0;
+    int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu)
     bool count = false;
     float last_ms = 0.f;
     uint64_t launches = 0;
 
-    DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink;
+    DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink, ghemi, ginv;
+    std::vector<double> g_inv_e1;  // 1/(exp+1) of the distinct glossy exponents of the scene
+    bool use_gtable = true;
     DevBuf<uint32_t> sph_meta, pln_meta, tri_meta, set_index, rows;
     DevBuf<int32_t> ray_hit;
     DevBuf<DevMaterial> materials;
@@ -172,7 +175,7 @@ int flux_ctx_destroy(flux_ctx *ctx) {
         ctx->ray_o.release(); ctx->ray_d.release(); ctx->ray_t.release(); ctx->sink.release();
         ctx->sph_meta.release(); ctx->pln_meta.release(); ctx->tri_meta.release(); ctx->set_index.release();
         ctx->rows.release(); ctx->ray_hit.release(); ctx->materials.release(); ctx->pixel.release();
-        ctx->disc.release(); ctx->counters.release(); ctx->work_counter.release();
+        ctx->disc.release(); ctx->counters.release(); ctx->work_counter.release(); ctx->ghemi.release(); ctx->ginv.release();
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);
         cudaStreamDestroy(ctx->stream);
@@ -180,6 +183,8 @@ int flux_ctx_destroy(flux_ctx *ctx) {
     delete ctx;
     return FLUX_OK;
 }
+
+static int build_glossy_table(flux_ctx *ctx);
 
 int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_config *cfg) {
     if (!ctx) return FLUX_ERR_INVALID;
@@ -226,7 +231,23 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         }
         d.exp = m.exp;
         d.inv_e1 = 1.0 / (m.exp + 1.0);  // samplers/src/lib.rs:135
+        d.gidx = 0;
         mats[i] = d;
+    }
+    // distinct glossy exponents -> columns of the lobe table (DevSamples::ghemi)
+    ctx->g_inv_e1.clear();
+    {
+        std::vector<double> exps;
+        for (uint32_t i = 0; i < s->n_materials; i++) {
+            if (mats[i].kind != FLUX_MAT_GLOSSY) continue;
+            size_t k = 0;
+            while (k < exps.size() && std::memcmp(&exps[k], &mats[i].exp, sizeof(double)) != 0) k++;
+            if (k == exps.size()) {
+                exps.push_back(mats[i].exp);
+                ctx->g_inv_e1.push_back(mats[i].inv_e1);
+            }
+            mats[i].gidx = (uint32_t)k;
+        }
     }
     // ---- spheres: SoA + bounding boxes as Sphere::new (shapes.rs:154-169) ----
     const uint32_t ns = s->n_spheres, np = s->n_planes, nt = s->n_triangles;
@@ -327,6 +348,31 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     if (ctx->have_samples && (ctx->ss.root != cfg->sample_root || ctx->ss.max_depth != cfg->max_trace_depth))
         ctx->have_samples = false;
     if (ctx->have_index && ctx->set_index.cap < (size_t)cam.W * cam.H) ctx->have_index = false;
+    if (ctx->have_samples) return build_glossy_table(ctx);  // exponents may have changed
+    ctx->ss.ghemi = nullptr;
+    ctx->ss.gk = 0;
+    return FLUX_OK;
+}
+
+// (Re)build the glossy lobe table for the current scene and sample sets.  Skipped (kernels fall back to
+// inline evaluation, same values) when the scene has no glossy material or the table would exceed 16 GiB.
+static int build_glossy_table(flux_ctx *ctx) {
+    ctx->ss.ghemi = nullptr;
+    ctx->ss.gk = 0;
+    const size_t gk = ctx->g_inv_e1.size();
+    if (!ctx->use_gtable || gk == 0 || !ctx->have_scene) return FLUX_OK;
+    const size_t elems = (size_t)ctx->ss.num_sets * gk * ctx->ss.n * 3;
+    if (elems * sizeof(double) > (16ull << 30)) return FLUX_OK;
+    CK(ctx->ghemi.reserve(elems));
+    CK(ctx->ginv.reserve(gk));
+    CK(cudaMemcpyAsync(ctx->ginv.p, ctx->g_inv_e1.data(), gk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_build_glossy_table(ctx->pixel.p, ctx->ss.n, ctx->ss.num_sets, (uint32_t)gk, ctx->ginv.p, ctx->ghemi.p,
+                              ctx->sm_count, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ss.ghemi = ctx->ghemi.p;
+    ctx->ss.gk = (uint32_t)gk;
     return FLUX_OK;
 }
 
@@ -364,7 +410,7 @@ int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t 
     if (max_depth) CK(cudaMemcpyAsync(ctx->hemi.p, hemi_xyz, n * num_sets * max_depth * 24, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_samples = true;
-    return FLUX_OK;
+    return build_glossy_table(ctx);
 }
 
 int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
@@ -392,7 +438,7 @@ int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->have_samples = true;
     ctx->have_index = true;
-    return FLUX_OK;
+    return build_glossy_table(ctx);
 }
 
 int flux_get_samples(flux_ctx *ctx, double *pixel_xy, double *disc_xy, double *hemi_xyz) {
@@ -480,7 +526,13 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     p.counters = ctx->counters.p;
     p.work_counter = ctx->work_counter.p;
     CK(cudaEventRecord(ctx->ev0, st));
-    launch_render(p, ctx->count, ctx->sm_count, st);
+    const bool regen_ok = regen_kernel_applicable(p);
+    if (ctx->kernel_mode == 2 && !regen_ok)
+        return fail(ctx, FLUX_ERR_INVALID, "render: regeneration kernel needs spp >= 64 and a sphere/plane scene that fits shared memory");
+    if (regen_ok && ctx->kernel_mode != 1)
+        launch_render_regen(p, ctx->count, ctx->sm_count, st);
+    else
+        launch_render(p, ctx->count, ctx->sm_count, st);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaGetLastError());
@@ -632,6 +684,19 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode) {
     if (!ctx) return FLUX_ERR_INVALID;
     if (mode < 0 || mode > 2) return fail(ctx, FLUX_ERR_INVALID, "flux_set_accel_mode: mode must be 0, 1 or 2");
     ctx->accel_mode = mode;
+    return FLUX_OK;
+}
+
+int flux_set_kernel_mode(flux_ctx *ctx, int mode) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0, 1 or 2");
+    ctx->kernel_mode = mode;
+    return FLUX_OK;
+}
+
+int flux_set_glossy_table(flux_ctx *ctx, int enable) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    ctx->use_gtable = enable != 0;
     return FLUX_OK;
 }
 

@@ -7,6 +7,11 @@
 // Camera::render for a list of rows (trace.rs:53-97).
 void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
 
+// Same result, scheduled for high sample counts: warp per pixel, in-warp path regeneration,
+// scene in shared memory (render_regen.cu).
+bool regen_kernel_applicable(const RenderParams &p);
+void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
+
 // Scene::hit on an explicit ray batch (scene.rs:156-160).
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
                        int sm_count, cudaStream_t stream);
@@ -16,6 +21,9 @@ void launch_generate_samples(uint64_t seed, uint32_t root, uint32_t max_depth, u
                              double2 *disc, double *hemi, cudaStream_t stream);
 void launch_generate_set_index(uint64_t seed, uint32_t H, uint32_t W, uint32_t num_sets, uint32_t *idx,
                                cudaStream_t stream);
+
+void launch_build_glossy_table(const double2 *pixel, uint32_t n, uint32_t num_sets, uint32_t gk, const double *inv_e1,
+                               double *ghemi, int sm_count, cudaStream_t stream);
 
 // FP64 issue-rate microbenchmark; returns total FP64 instructions executed.
 double launch_fp64_peak(int sm_count, int iters, double *sink, cudaStream_t stream);

@@ -19,7 +19,7 @@ enum { KIND_SPHERE = 0, KIND_PLANE = 1, KIND_TRI = 2 };
 
 struct DevMaterial {
     uint32_t kind;   // FLUX_MAT_*
-    uint32_t _pad;
+    uint32_t gidx;   // glossy: index of this material's exponent in the lobe table (DevSamples::ghemi)
     double c[3];     // matte: (cd*kd)*INV_PI; emissive: color*power; reflective/glossy: cs*ks
     double exp;      // glossy exponent
     double inv_e1;   // 1.0/(exp+1.0), samplers/src/lib.rs:135
@@ -60,6 +60,10 @@ struct DevSamples {
     const double2 *pixel;   // [set][i]
     const double2 *disc;    // [set][i]
     const double *hemi;     // [set][depth][i][3]
+    // glossy lobe table: to_unit_hemi(pixel_sets[set][i], exp_k) for the K distinct glossy exponents of the
+    // scene, [set][k][i][3]; null when not built (then the kernels evaluate it inline)
+    const double *ghemi;
+    uint32_t gk;
 };
 
 struct RenderParams {

@@ -44,17 +44,16 @@ __device__ __forceinline__ V3 to_unit_hemi_dev(double px, double py, double inv_
     return normalize3(mk3(pu, pv, pw));
 }
 
-// Reflective + GlossySpecular: materials.rs:57-71 + brdf.rs:55-78.
-// lobe multiplies the per-material constant cs*ks to give f.
-__device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, double sqy, double ex, double inv_e1,
-                                              V3 &wi, double &weight, double &lobe, bool &flipped) {
+// Reflective + GlossySpecular: materials.rs:57-71 + brdf.rs:55-78, given hs = to_unit_hemi(pixel_sample, exp)
+// (brdf.rs:64).  lobe multiplies the per-material constant cs*ks to give f.
+__device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, double ex, V3 &wi, double &weight,
+                                                 double &lobe, bool &flipped) {
     V3 wo = dir * -1.0;
     double ndotwo = dot3(normal, wo);
     V3 r = neg3(wo) + normal * ndotwo * 2.0;
     V3 w = r;
     V3 u = normalize3(cross3(mk3(0.00424, 1.0, 0.00764), w));
     V3 v = cross3(u, w);
-    V3 hs = to_unit_hemi_dev(sqx, sqy, inv_e1);
     V3 wi0 = (u * hs.x + v * hs.y) + w * hs.z;
     flipped = dot3(normal, wi0) < 0.0;
     if (flipped)
@@ -64,4 +63,9 @@ __device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, dou
     lobe = pow(dot3(r, wi), ex);
     double pdf = lobe * dot3(normal, wi);
     weight = dot3(normal, wi) / pdf;
+}
+
+__device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, double sqy, double ex, double inv_e1,
+                                              V3 &wi, double &weight, double &lobe, bool &flipped) {
+    glossy_sample_hs(normal, dir, to_unit_hemi_dev(sqx, sqy, inv_e1), ex, wi, weight, lobe, flipped);
 }

@@ -17,6 +17,7 @@
 //
 // One CTA per (set, grid).  Permutations live in shared memory as u16.
 #include "flux_kernels.cuh"
+#include "flux_shade.cuh"
 
 namespace {
 
@@ -158,7 +159,32 @@ __global__ void __launch_bounds__(256) generate_set_index_kernel(uint64_t seed, 
     for (uint32_t col = threadIdx.x; col < W; col += blockDim.x) idx[(size_t)row * W + col] = rperm[col % num_sets];
 }
 
+// Glossy lobe table: ghemi[set][k][i] = to_unit_hemi(pixel_sets[set][i], exp_k) (samplers/src/lib.rs:133-142 as
+// called at brdf.rs:64).  The same device function the render kernels would call inline, so the table holds
+// bit-identical values; it removes sincos + pow + sqrt + 3 divisions from every glossy bounce.
+__global__ void __launch_bounds__(256) build_glossy_table_kernel(const double2 *__restrict__ pixel, uint32_t n,
+                                                                 uint32_t num_sets, uint32_t gk,
+                                                                 const double *__restrict__ inv_e1,
+                                                                 double *__restrict__ ghemi) {
+    const size_t total = (size_t)num_sets * gk * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(t % n);
+        const uint32_t k = (uint32_t)((t / n) % gk);
+        const size_t set = t / ((size_t)n * gk);
+        const double2 p = pixel[set * n + i];
+        const V3 h = to_unit_hemi_dev(p.x, p.y, inv_e1[k]);
+        ghemi[3 * t + 0] = h.x;
+        ghemi[3 * t + 1] = h.y;
+        ghemi[3 * t + 2] = h.z;
+    }
+}
+
 }  // namespace
+
+void launch_build_glossy_table(const double2 *pixel, uint32_t n, uint32_t num_sets, uint32_t gk, const double *inv_e1,
+                               double *ghemi, int sm_count, cudaStream_t stream) {
+    build_glossy_table_kernel<<<sm_count * 8, 256, 0, stream>>>(pixel, n, num_sets, gk, inv_e1, ghemi);
+}
 
 void launch_generate_samples(uint64_t seed, uint32_t root, uint32_t max_depth, uint32_t num_sets, double2 *pixel,
                              double2 *disc, double *hemi, cudaStream_t stream) {

@@ -156,6 +156,12 @@ class GpuContext:
     def set_accel_mode(self, mode: int):
         self._ck(self._lib.flux_set_accel_mode(self._ctx, mode))
 
+    def set_kernel_mode(self, mode: int):
+        self._ck(self._lib.flux_set_kernel_mode(self._ctx, mode))
+
+    def set_glossy_table(self, on: bool):
+        self._ck(self._lib.flux_set_glossy_table(self._ctx, 1 if on else 0))
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self._ck(self._lib.flux_measure_fp64_peak(self._ctx, C.byref(v)))

@@ -240,6 +240,18 @@ int flux_launch_count(flux_ctx *ctx, uint64_t *n);
  * 2 = BVH.  Results are identical by construction; used by parity tests. */
 int flux_set_accel_mode(flux_ctx *ctx, int mode);
 
+/* Force the render kernel variant: 0 = auto, 1 = direct (lane group per pixel), 2 = regeneration
+ * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene).
+ * Both compute the same per-sample radiance; they differ only in the order of the per-pixel
+ * sum (last bits).  Used by parity tests and A/B timing. */
+int flux_set_kernel_mode(flux_ctx *ctx, int mode);
+
+/* Enable (default) / disable the glossy lobe table: to_unit_hemi(pixel sample, reflect_exponent)
+ * (brdf.rs:64, samplers/src/lib.rs:133-142) tabulated per sample and distinct exponent when the sample
+ * sets are installed, instead of being evaluated at every glossy bounce.  Same device function, same bits.
+ * Takes effect at the next flux_set_scene / flux_set_samples / flux_generate_samples. */
+int flux_set_glossy_table(flux_ctx *ctx, int enable);
+
 /* Unfused FP64 issue-rate microbenchmark (the roofline denominator of
  * SURVEY.md §8d / H8): returns 1e9 FP64 instr/s for dependent DADD/DMUL chains
  * over the whole device. */

@@ -259,3 +259,72 @@ def test_gpu_converged_demo2_matches_reference_png(gpu_ctx, demo2):
     print(f"demo2 @4096spp vs demo.png: rmse {rmse:.5f}, channel mean ratio {ratio}")
     assert rmse < 0.015, rmse
     assert np.all(np.abs(ratio - 1.0) < 0.005), ratio
+
+
+# ---- kernel variants: direct (render.cu) vs regeneration (render_regen.cu) ---------------------------------
+@pytest.mark.parametrize("scene_name", ["demo1", "demo2", "mixed", "deterministic"])
+def test_regen_kernel_matches_oracle_and_direct(gpu_ctx, demo1, demo2, scene_name):
+    """spp >= 64 selects the warp-per-pixel regeneration kernel.  Same per-sample arithmetic as the
+    direct kernel: both must match the oracle; event counters must be identical between the two."""
+    sd = {"demo1": demo1.with_size(96, 72), "demo2": demo2.with_size(96, 72), "mixed": Hp.mixed_material_scene(),
+          "deterministic": Hp.deterministic_scene()}[scene_name]
+    W, H = sd.output_settings.image_width, sd.output_settings.image_height
+    cfg = JobConfiguration(9, 5, 50)  # 81 spp: not a multiple of 32 -> exercises the pixel tail
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(31, cfg, W, H)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    imgs, cns = {}, {}
+    try:
+        for mode in (1, 2):
+            gpu_ctx.set_kernel_mode(mode)
+            gpu_ctx.enable_counters(True)
+            gpu_ctx.reset_counters()
+            imgs[mode] = gpu_ctx.render_rows(0, H - 1, W)
+            cns[mode] = gpu_ctx.counters()
+            gpu_ctx.enable_counters(False)
+            again = gpu_ctx.render_rows(0, H - 1, W)  # uninstrumented instantiation, and run-to-run determinism
+            assert np.array_equal(imgs[mode].view(np.uint64), again.view(np.uint64))
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.enable_counters(False)
+    ref, cn_o = O.render_rows(flat, cfg, ss, 0, H - 1, counters=True)
+    tol = 1e-13 if scene_name == "deterministic" else RADIANCE_RTOL
+    assert Hp.rel_err(imgs[1], ref) <= tol
+    assert Hp.rel_err(imgs[2], ref) <= tol
+    assert cns[1] == cns[2]
+    for k, v in cn_o.items():
+        assert abs(cns[2][k] - v) <= max(2, 1e-6 * v), (k, cns[2][k], v)
+
+
+def test_regen_kernel_sharding_bitwise(gpu_ctx, demo2):
+    sd = demo2.with_size(64, 40)
+    cfg = JobConfiguration(8, 5, 50)
+    ss = Hp.oracle_samples(4, cfg, 64, 40)
+    Hp.upload(gpu_ctx, sd.flatten(), cfg, ss)
+    from flux_b200.worker import shard_rows
+    full = gpu_ctx.render_rows(0, 39, 64)
+    for world in (2, 8):
+        parts = np.empty_like(full)
+        for rank in range(world):
+            rows = shard_rows(40, 4, rank, world)
+            if len(rows):
+                parts[rows] = gpu_ctx.render_row_list(rows, 64)
+        assert np.array_equal(full.view(np.uint64), parts.view(np.uint64))
+
+
+def test_glossy_table_is_bit_identical_to_inline(gpu_ctx, demo2):
+    """The glossy lobe table holds to_unit_hemi(pixel sample, exponent) computed by the same device function
+    the kernels call inline: rendering with and without it must agree bit for bit."""
+    sd = demo2.with_size(80, 60)
+    cfg = JobConfiguration(8, 5, 50)
+    ss = Hp.oracle_samples(8, cfg, 80, 60)
+    imgs = []
+    try:
+        for on in (False, True):
+            gpu_ctx.set_glossy_table(on)
+            Hp.upload(gpu_ctx, sd.flatten(), cfg, ss)
+            imgs.append(gpu_ctx.render_rows(0, 59, 80))
+    finally:
+        gpu_ctx.set_glossy_table(True)
+    assert np.array_equal(imgs[0].view(np.uint64), imgs[1].view(np.uint64))
+    assert Hp.rel_err(imgs[1], O.render_rows(sd.flatten(), cfg, ss, 0, 59)) <= RADIANCE_RTOL
