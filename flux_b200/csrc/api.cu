@@ -54,7 +54,7 @@ struct flux_ctx {
     DevScene scene{};
     DevSamples ss{};
     int accel_mode = 0;
-    int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu)
+    int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu), 3 wavefront (render_wave.cu)
     bool count = false;
     float last_ms = 0.f;
     uint64_t launches = 0;
@@ -529,7 +529,12 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     const bool regen_ok = regen_kernel_applicable(p);
     if (ctx->kernel_mode == 2 && !regen_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: regeneration kernel needs spp >= 64 and a sphere/plane scene that fits shared memory");
-    if (regen_ok && ctx->kernel_mode != 1)
+    const bool wave_ok = wave_kernel_applicable(p);
+    if (ctx->kernel_mode == 3 && !wave_ok)
+        return fail(ctx, FLUX_ERR_INVALID, "render: wavefront kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
+    if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
+        launch_render_wave(p, ctx->count, ctx->sm_count, st);
+    else if (regen_ok && ctx->kernel_mode != 1)
         launch_render_regen(p, ctx->count, ctx->sm_count, st);
     else
         launch_render(p, ctx->count, ctx->sm_count, st);
@@ -689,7 +694,7 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode) {
 
 int flux_set_kernel_mode(flux_ctx *ctx, int mode) {
     if (!ctx) return FLUX_ERR_INVALID;
-    if (mode < 0 || mode > 2) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0..3");
     ctx->kernel_mode = mode;
     return FLUX_OK;
 }

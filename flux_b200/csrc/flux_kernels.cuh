@@ -12,6 +12,11 @@ void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t
 bool regen_kernel_applicable(const RenderParams &p);
 void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
 
+// Same result, block-local wavefront for spp >= 4096: CTA per pixel, path slots in shared memory, compacted
+// (slot, sphere) candidate pairs, material-sorted shading (render_wave.cu).
+bool wave_kernel_applicable(const RenderParams &p);
+void launch_render_wave(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
+
 // Scene::hit on an explicit ray batch (scene.rs:156-160).
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
                        int sm_count, cudaStream_t stream);

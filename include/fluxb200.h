@@ -241,9 +241,10 @@ int flux_launch_count(flux_ctx *ctx, uint64_t *n);
 int flux_set_accel_mode(flux_ctx *ctx, int mode);
 
 /* Force the render kernel variant: 0 = auto, 1 = direct (lane group per pixel), 2 = regeneration
- * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene).
- * Both compute the same per-sample radiance; they differ only in the order of the per-pixel
- * sum (last bits).  Used by parity tests and A/B timing. */
+ * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene),
+ * 3 = block-local wavefront (CTA per pixel, compacted candidate pairs, material-sorted shading;
+ * needs spp >= 4096, depth <= 8).  All compute the same per-sample radiance; they differ only in
+ * the order of the per-pixel sum (last bits).  Used by parity tests and A/B timing. */
 int flux_set_kernel_mode(flux_ctx *ctx, int mode);
 
 /* Enable (default) / disable the glossy lobe table: to_unit_hemi(pixel sample, reflect_exponent)

@@ -328,3 +328,52 @@ def test_glossy_table_is_bit_identical_to_inline(gpu_ctx, demo2):
         gpu_ctx.set_glossy_table(True)
     assert np.array_equal(imgs[0].view(np.uint64), imgs[1].view(np.uint64))
     assert Hp.rel_err(imgs[1], O.render_rows(sd.flatten(), cfg, ss, 0, 59)) <= RADIANCE_RTOL
+
+
+@pytest.mark.parametrize("scene_name", ["demo2", "mixed", "deterministic"])
+def test_wavefront_kernel_matches_oracle_and_regen(gpu_ctx, demo2, scene_name):
+    """spp >= 4096 selects the block-local wavefront kernel (CTA per pixel, compacted candidate pairs,
+    material-sorted shading).  Same per-sample arithmetic: must match the oracle; event counters must be
+    identical to the regeneration kernel's."""
+    sd = {"demo2": demo2.with_size(24, 18), "mixed": Hp.mixed_material_scene(24, 16),
+          "deterministic": Hp.deterministic_scene(24, 16)}[scene_name]
+    W, H = sd.output_settings.image_width, sd.output_settings.image_height
+    cfg = JobConfiguration(65, 5, 50)  # 4225 spp: not a multiple of 256 -> exercises the drain tail
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(41, cfg, W, H)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    imgs, cns = {}, {}
+    try:
+        for mode in (2, 3):
+            gpu_ctx.set_kernel_mode(mode)
+            gpu_ctx.enable_counters(True)
+            gpu_ctx.reset_counters()
+            imgs[mode] = gpu_ctx.render_rows(0, H - 1, W)
+            cns[mode] = gpu_ctx.counters()
+            gpu_ctx.enable_counters(False)
+            again = gpu_ctx.render_rows(0, H - 1, W)
+            assert np.array_equal(imgs[mode].view(np.uint64), again.view(np.uint64))
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.enable_counters(False)
+    ref, cn_o = O.render_rows(flat, cfg, ss, 0, H - 1, counters=True)
+    tol = 1e-12 if scene_name == "deterministic" else RADIANCE_RTOL
+    assert Hp.rel_err(imgs[3], ref) <= tol
+    assert Hp.rel_err(imgs[2], ref) <= tol
+    assert cns[2] == cns[3]
+    for k, v in cn_o.items():
+        assert abs(cns[3][k] - v) <= max(2, 1e-6 * v), (k, cns[3][k], v)
+
+
+def test_wavefront_kernel_sharding_bitwise(gpu_ctx, demo2):
+    sd = demo2.with_size(16, 12)
+    cfg = JobConfiguration(64, 5, 50)
+    gpu_ctx.set_scene(sd.flatten(), cfg)
+    gpu_ctx.generate_samples(3, 16)
+    from flux_b200.worker import shard_rows
+    full = gpu_ctx.render_rows(0, 11, 16)
+    parts = np.empty_like(full)
+    for rank in range(4):
+        rows = shard_rows(12, 2, rank, 4)
+        parts[rows] = gpu_ctx.render_row_list(rows, 16)
+    assert np.array_equal(full.view(np.uint64), parts.view(np.uint64))
