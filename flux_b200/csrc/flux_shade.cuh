@@ -15,9 +15,9 @@
 // (cd*kd)*INV_PI precomputed on the host (same IEEE products).
 __device__ __forceinline__ void matte_sample(V3 normal, V3 hemi, V3 &wi, double &weight) {
     V3 w = normal;
-    V3 v = normalize3(cross3(mk3(0.0034, 1.0, 0.0071), w));
+    V3 v = normalize3_dev(cross3(mk3(0.0034, 1.0, 0.0071), w));
     V3 u = cross3(v, w);
-    wi = normalize3((hemi.x * u + hemi.y * v) + hemi.z * w);
+    wi = normalize3_dev((hemi.x * u + hemi.y * v) + hemi.z * w);
     double pdf = dot3(normal, wi) * FLUX_INV_PI;
     double ndotwi = dot3(normal, wi);
     weight = ndotwi / pdf;
@@ -41,7 +41,7 @@ __device__ __forceinline__ V3 to_unit_hemi_dev(double px, double py, double inv_
     double pu = sin_theta * cos_phi;
     double pv = sin_theta * sin_phi;
     double pw = cos_theta;
-    return normalize3(mk3(pu, pv, pw));
+    return normalize3_dev(mk3(pu, pv, pw));
 }
 
 // Reflective + GlossySpecular: materials.rs:57-71 + brdf.rs:55-78, given hs = to_unit_hemi(pixel_sample, exp)
@@ -52,7 +52,7 @@ __device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, doubl
     double ndotwo = dot3(normal, wo);
     V3 r = neg3(wo) + normal * ndotwo * 2.0;
     V3 w = r;
-    V3 u = normalize3(cross3(mk3(0.00424, 1.0, 0.00764), w));
+    V3 u = normalize3_dev(cross3(mk3(0.00424, 1.0, 0.00764), w));
     V3 v = cross3(u, w);
     V3 wi0 = (u * hs.x + v * hs.y) + w * hs.z;
     flipped = dot3(normal, wi0) < 0.0;
