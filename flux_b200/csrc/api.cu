@@ -6,12 +6,14 @@
 // samples), flux_set_samples / flux_generate_samples = MasterSampleSets::new,
 // flux_render_rows = Camera::render.
 #include "../../include/fluxb200.h"
+#include "flux_bvh.cuh"
 #include "flux_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
@@ -68,6 +70,12 @@ struct flux_ctx {
     DevBuf<double2> pixel, disc;
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned int> work_counter;
+    // BVH extension (flux_bvh.cuh)
+    DevBuf<BvhNode4> bvh_nodes;
+    DevBuf<SphRec> bvh_sph;
+    DevBuf<TriRec> bvh_tri;
+    DevBuf<uint32_t> bvh_prims, bvh_linear;
+    uint32_t bvh_depth = 0, bvh_leaf = 0;
 };
 
 namespace {
@@ -101,6 +109,48 @@ void camera_basis(V3 eye, V3 look_at, V3 up, V3 &u, V3 &v, V3 &w) {
     w = normalize3(eye - look_at);
     u = normalize3(cross3(up, w));
     v = cross3(w, u);
+}
+
+// spheres as SoA + bounding boxes as Sphere::new (shapes.rs:154-169)
+void flatten_spheres(const flux_scene_flat *s, std::vector<double> &sph, std::vector<uint32_t> &sph_meta) {
+    const uint32_t ns = s->n_spheres;
+    sph.assign((size_t)SPH_FIELDS * ns, 0.0);
+    sph_meta.assign((size_t)2 * ns, 0u);
+    for (uint32_t i = 0; i < ns; i++) {
+        const double *c = s->sphere_center + 3 * (size_t)i;
+        const double r = s->sphere_radius[i];
+        sph[(size_t)SPH_CX * ns + i] = c[0];
+        sph[(size_t)SPH_CY * ns + i] = c[1];
+        sph[(size_t)SPH_CZ * ns + i] = c[2];
+        sph[(size_t)SPH_R * ns + i] = r;
+        sph[(size_t)SPH_RR * ns + i] = r * r;                       // shapes.rs:179
+        sph[(size_t)SPH_INV * ns + i] = s->sphere_invert[i] ? -1.0 : 1.0;  // shapes.rs:181
+        sph[(size_t)SPH_C0X * ns + i] = c[0] - r;
+        sph[(size_t)SPH_C0Y * ns + i] = c[1] - r;
+        sph[(size_t)SPH_C0Z * ns + i] = c[2] - r;
+        sph[(size_t)SPH_C1X * ns + i] = c[0] + r;
+        sph[(size_t)SPH_C1Y * ns + i] = c[1] + r;
+        sph[(size_t)SPH_C1Z * ns + i] = c[2] + r;
+        sph_meta[i] = s->sphere_shape_id[i];
+        sph_meta[ns + i] = s->sphere_material[i];
+    }
+}
+
+// triangles (EXTENSION) as SoA: v0, e1 = v1 - v0, e2 = v2 - v0
+void flatten_triangles(const flux_scene_flat *s, std::vector<double> &tri, std::vector<uint32_t> &tri_meta) {
+    const uint32_t nt = s->n_triangles;
+    tri.assign((size_t)TRI_FIELDS * nt, 0.0);
+    tri_meta.assign((size_t)2 * nt, 0u);
+    for (uint32_t i = 0; i < nt; i++) {
+        for (int k = 0; k < 3; k++) {
+            const double v0 = s->tri_v0[3 * (size_t)i + k];
+            tri[(size_t)(TRI_V0X + k) * nt + i] = v0;
+            tri[(size_t)(TRI_E1X + k) * nt + i] = s->tri_v1[3 * (size_t)i + k] - v0;
+            tri[(size_t)(TRI_E2X + k) * nt + i] = s->tri_v2[3 * (size_t)i + k] - v0;
+        }
+        tri_meta[i] = s->tri_shape_id[i];
+        tri_meta[nt + i] = s->tri_material[i];
+    }
 }
 
 V3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
@@ -176,6 +226,7 @@ int flux_ctx_destroy(flux_ctx *ctx) {
         ctx->sph_meta.release(); ctx->pln_meta.release(); ctx->tri_meta.release(); ctx->set_index.release();
         ctx->rows.release(); ctx->ray_hit.release(); ctx->materials.release(); ctx->pixel.release();
         ctx->disc.release(); ctx->counters.release(); ctx->work_counter.release(); ctx->ghemi.release(); ctx->ginv.release();
+        ctx->bvh_nodes.release(); ctx->bvh_sph.release(); ctx->bvh_tri.release(); ctx->bvh_prims.release(); ctx->bvh_linear.release();
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);
         cudaStreamDestroy(ctx->stream);
@@ -251,26 +302,9 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     }
     // ---- spheres: SoA + bounding boxes as Sphere::new (shapes.rs:154-169) ----
     const uint32_t ns = s->n_spheres, np = s->n_planes, nt = s->n_triangles;
-    std::vector<double> sph((size_t)SPH_FIELDS * ns);
-    std::vector<uint32_t> sph_meta((size_t)2 * ns);
-    for (uint32_t i = 0; i < ns; i++) {
-        const double *c = s->sphere_center + 3 * i;
-        const double r = s->sphere_radius[i];
-        sph[(size_t)SPH_CX * ns + i] = c[0];
-        sph[(size_t)SPH_CY * ns + i] = c[1];
-        sph[(size_t)SPH_CZ * ns + i] = c[2];
-        sph[(size_t)SPH_R * ns + i] = r;
-        sph[(size_t)SPH_RR * ns + i] = r * r;                       // shapes.rs:179
-        sph[(size_t)SPH_INV * ns + i] = s->sphere_invert[i] ? -1.0 : 1.0;  // shapes.rs:181
-        sph[(size_t)SPH_C0X * ns + i] = c[0] - r;
-        sph[(size_t)SPH_C0Y * ns + i] = c[1] - r;
-        sph[(size_t)SPH_C0Z * ns + i] = c[2] - r;
-        sph[(size_t)SPH_C1X * ns + i] = c[0] + r;
-        sph[(size_t)SPH_C1Y * ns + i] = c[1] + r;
-        sph[(size_t)SPH_C1Z * ns + i] = c[2] + r;
-        sph_meta[i] = s->sphere_shape_id[i];
-        sph_meta[ns + i] = s->sphere_material[i];
-    }
+    std::vector<double> sph;
+    std::vector<uint32_t> sph_meta;
+    flatten_spheres(s, sph, sph_meta);
     std::vector<double> pln((size_t)PLN_FIELDS * np);
     std::vector<uint32_t> pln_meta((size_t)2 * np);
     for (uint32_t i = 0; i < np; i++) {
@@ -281,18 +315,9 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         pln_meta[i] = s->plane_shape_id[i];
         pln_meta[np + i] = s->plane_material[i];
     }
-    std::vector<double> tri((size_t)TRI_FIELDS * nt);
-    std::vector<uint32_t> tri_meta((size_t)2 * nt);
-    for (uint32_t i = 0; i < nt; i++) {
-        for (int k = 0; k < 3; k++) {
-            const double v0 = s->tri_v0[3 * (size_t)i + k];
-            tri[(size_t)(TRI_V0X + k) * nt + i] = v0;
-            tri[(size_t)(TRI_E1X + k) * nt + i] = s->tri_v1[3 * (size_t)i + k] - v0;
-            tri[(size_t)(TRI_E2X + k) * nt + i] = s->tri_v2[3 * (size_t)i + k] - v0;
-        }
-        tri_meta[i] = s->tri_shape_id[i];
-        tri_meta[nt + i] = s->tri_material[i];
-    }
+    std::vector<double> tri;
+    std::vector<uint32_t> tri_meta;
+    flatten_triangles(s, tri, tri_meta);
     CK(ctx->materials.reserve(mats.size()));
     CK(ctx->sph.reserve(sph.size()));
     CK(ctx->sph_meta.reserve(sph_meta.size()));
@@ -325,6 +350,39 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     sc.tri = ctx->tri.p;
     sc.tri_meta = ctx->tri_meta.p;
     sc.materials = ctx->materials.p;
+
+    // ---- acceleration structure (EXTENSION): the reference scans linearly (scene.rs:156-160); scenes beyond
+    // FLUX_LINEAR_LIMIT bounded shapes get a BVH that returns the same answer (flux_bvh.cuh) ----
+    ctx->bvh_depth = ctx->bvh_leaf = 0;
+    const bool want_bvh = (ns + nt > 0) && (ctx->accel_mode == 2 || (ctx->accel_mode == 0 && (uint64_t)ns + nt > FLUX_LINEAR_LIMIT));
+    if (want_bvh) {
+        BvhBuild bb;
+        std::string berr;
+        if (!build_bvh4(sph.data(), sph_meta.data(), ns, tri.data(), tri_meta.data(), s->tri_v1, s->tri_v2, nt, bb, berr))
+            return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: " + berr);
+        CK(ctx->bvh_nodes.reserve(bb.nodes.size()));
+        CK(ctx->bvh_sph.reserve(bb.sph.size()));
+        CK(ctx->bvh_tri.reserve(bb.tri.size()));
+        CK(ctx->bvh_prims.reserve(bb.prims.size()));
+        CK(ctx->bvh_linear.reserve(bb.linear.size()));
+        CK(up(ctx->bvh_nodes.p, bb.nodes.data(), bb.nodes.size() * sizeof(BvhNode4)));
+        CK(up(ctx->bvh_sph.p, bb.sph.data(), bb.sph.size() * sizeof(SphRec)));
+        CK(up(ctx->bvh_tri.p, bb.tri.data(), bb.tri.size() * sizeof(TriRec)));
+        CK(up(ctx->bvh_prims.p, bb.prims.data(), bb.prims.size() * sizeof(uint32_t)));
+        CK(up(ctx->bvh_linear.p, bb.linear.data(), bb.linear.size() * sizeof(uint32_t)));
+        CK(cudaStreamSynchronize(ctx->stream));
+        sc.use_bvh = 1;
+        sc.bvh_nodes = ctx->bvh_nodes.p;
+        sc.bvh_n_nodes = (uint32_t)bb.nodes.size();
+        sc.bvh_prims = ctx->bvh_prims.p;
+        sc.bvh_sph = ctx->bvh_sph.p;
+        sc.bvh_tri = ctx->bvh_tri.p;
+        sc.bvh_linear = ctx->bvh_linear.p;
+        sc.bvh_n_linear = (uint32_t)bb.linear.size();
+        sc.bvh_extent = bb.extent;
+        ctx->bvh_depth = bb.depth;
+        ctx->bvh_leaf = bb.leaf_size;
+    }
 
     // ---- camera: CameraBasis::new (scene.rs:29-34) + render() prologue (trace.rs:54-60) ----
     DevCamera &cam = ctx->cam;
@@ -689,6 +747,81 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode) {
     if (!ctx) return FLUX_ERR_INVALID;
     if (mode < 0 || mode > 2) return fail(ctx, FLUX_ERR_INVALID, "flux_set_accel_mode: mode must be 0, 1 or 2");
     ctx->accel_mode = mode;
+    return FLUX_OK;
+}
+
+int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
+    if (!s || !out) return FLUX_ERR_INVALID;
+    const uint32_t ns = s->n_spheres, nt = s->n_triangles;
+    if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
+        (nt && (!s->tri_v0 || !s->tri_v1 || !s->tri_v2 || !s->tri_shape_id || !s->tri_material)))
+        return FLUX_ERR_INVALID;
+    std::vector<double> sph, tri;
+    std::vector<uint32_t> sph_meta, tri_meta;
+    flatten_spheres(s, sph, sph_meta);
+    flatten_triangles(s, tri, tri_meta);
+    BvhBuild bb;
+    std::string err;
+    if (!build_bvh4(sph.data(), sph_meta.data(), ns, tri.data(), tri_meta.data(), s->tri_v1, s->tri_v2, nt, bb, err)) {
+        g_create_error = err;
+        return FLUX_ERR_INVALID;
+    }
+    uint64_t violations = 0;
+    std::vector<uint32_t> seen_s(ns, 0), seen_t(nt, 0);
+    for (uint32_t i : bb.linear) seen_s[i]++;
+    // walk the tree: (node, slot box of the parent) pairs
+    struct Job { uint32_t ref; double lo[3], hi[3]; };
+    std::vector<Job> stack;
+    const double inf = std::numeric_limits<double>::infinity();
+    if (!bb.nodes.empty()) {
+        Job j; j.ref = 0;
+        for (int k = 0; k < 3; k++) j.lo[k] = -inf, j.hi[k] = inf;
+        stack.push_back(j);
+    }
+    while (!stack.empty()) {
+        const Job j = stack.back();
+        stack.pop_back();
+        if (j.ref & BVH_LEAF) {
+            const uint32_t off = (j.ref & 0x7FFFFFFFu) >> 3, cnt = (j.ref & 7u) + 1u;
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t pr = bb.prims[off + k], idx = pr & 0x3FFFFFFFu;
+                double lo[3], hi[3];
+                if ((pr >> 30) == KIND_SPHERE) {
+                    seen_s[idx]++;
+                    const SphRec &q = bb.sph[idx];
+                    lo[0] = std::min(q.c0x, q.c1x); hi[0] = std::max(q.c0x, q.c1x);
+                    lo[1] = std::min(q.c0y, q.c1y); hi[1] = std::max(q.c0y, q.c1y);
+                    lo[2] = std::min(q.c0z, q.c1z); hi[2] = std::max(q.c0z, q.c1z);
+                } else {
+                    seen_t[idx]++;
+                    for (int a = 0; a < 3; a++) {
+                        const double v0 = s->tri_v0[3 * (size_t)idx + a], v1 = s->tri_v1[3 * (size_t)idx + a], v2 = s->tri_v2[3 * (size_t)idx + a];
+                        lo[a] = std::min({v0, v1, v2});
+                        hi[a] = std::max({v0, v1, v2});
+                    }
+                }
+                for (int a = 0; a < 3; a++)
+                    if (!(j.lo[a] < lo[a] && hi[a] < j.hi[a])) violations++;   // strictly inside: the padding
+            }
+            continue;
+        }
+        const BvhNode4 &n = bb.nodes[j.ref];
+        for (int c = 0; c < 4; c++) {
+            if (n.child[c] == BVH_EMPTY) continue;
+            Job q; q.ref = n.child[c];
+            for (int a = 0; a < 3; a++) {
+                q.lo[a] = n.lo[a][c]; q.hi[a] = n.hi[a][c];
+                if (!(j.lo[a] <= q.lo[a] && q.hi[a] <= j.hi[a])) violations++;
+            }
+            stack.push_back(q);
+        }
+    }
+    uint64_t miscount = 0;
+    for (uint32_t v : seen_s) miscount += v != 1;
+    for (uint32_t v : seen_t) miscount += v != 1;
+    out[0] = bb.nodes.size(); out[1] = bb.depth; out[2] = bb.leaf_size; out[3] = bb.linear.size();
+    out[4] = bb.prims.size(); out[5] = violations; out[6] = miscount;
+    out[7] = ((uint64_t)ns + nt > FLUX_LINEAR_LIMIT) ? 1 : 0;
     return FLUX_OK;
 }
 

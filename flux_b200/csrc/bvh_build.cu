@@ -1,0 +1,271 @@
+// bvh_build.cu — host-side builder of the 4-wide BVH (EXTENSION; see flux_bvh.cuh for the
+// exactness argument).  Object-median splits on the longest axis of the centroid bounds: the tree is
+// balanced, so its depth — and with it the traversal stack a thread needs — is known in advance
+// (3 * levels + 1 <= BVH_STACK; the leaf size is raised until that holds).  Each 4-wide node is made by
+// splitting a range in two and each half in two again.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <string>
+
+#include "flux_bvh.cuh"
+
+namespace {
+
+struct Box {
+    double lo[3], hi[3];
+    void reset() {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::numeric_limits<double>::infinity();
+            hi[k] = -std::numeric_limits<double>::infinity();
+        }
+    }
+    void grow(const Box &b) {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], b.lo[k]);
+            hi[k] = std::max(hi[k], b.hi[k]);
+        }
+    }
+};
+
+struct Item {
+    Box box;
+    double c[3];      // centroid (split key only)
+    uint32_t ref;     // (kind << 30) | index
+};
+
+struct Builder {
+    std::vector<Item> items;
+    BvhBuild *out;
+    uint32_t leaf_size;
+    double pad;
+
+    Box bounds(uint32_t a, uint32_t b) const {
+        Box x;
+        x.reset();
+        for (uint32_t i = a; i < b; i++) x.grow(items[i].box);
+        return x;
+    }
+    // split [a,b) at the object median of the longest centroid axis; returns the middle
+    uint32_t split(uint32_t a, uint32_t b) {
+        double lo[3], hi[3];
+        for (int k = 0; k < 3; k++) lo[k] = std::numeric_limits<double>::infinity(), hi[k] = -lo[k];
+        for (uint32_t i = a; i < b; i++)
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], items[i].c[k]);
+                hi[k] = std::max(hi[k], items[i].c[k]);
+            }
+        int ax = 0;
+        for (int k = 1; k < 3; k++)
+            if (hi[k] - lo[k] > hi[ax] - lo[ax]) ax = k;
+        const uint32_t mid = a + (b - a + 1) / 2;
+        std::nth_element(items.begin() + a, items.begin() + mid, items.begin() + b, [ax](const Item &p, const Item &q) {
+            return p.c[ax] < q.c[ax] || (p.c[ax] == q.c[ax] && p.ref < q.ref);
+        });
+        return mid;
+    }
+    uint32_t make_leaf(uint32_t a, uint32_t b) {
+        const uint32_t off = (uint32_t)out->prims.size();
+        for (uint32_t i = a; i < b; i++) out->prims.push_back(items[i].ref);
+        return BVH_LEAF | (off << 3) | (b - a - 1);
+    }
+    void set_child(uint32_t node, int slot, uint32_t ref, const Box &bx) {
+        BvhNode4 &n = out->nodes[node];
+        n.child[slot] = ref;
+        for (int k = 0; k < 3; k++) {
+            n.lo[k][slot] = bx.lo[k] - pad;
+            n.hi[k][slot] = bx.hi[k] + pad;
+        }
+    }
+    // builds the subtree over [a,b) (b - a > leaf_size) and returns its node index; level = depth of this node
+    uint32_t build_node(uint32_t a, uint32_t b, uint32_t level) {
+        const uint32_t me = (uint32_t)out->nodes.size();
+        out->nodes.emplace_back();
+        out->depth = std::max(out->depth, level + 1);
+        {
+            BvhNode4 &n = out->nodes[me];
+            for (int s = 0; s < 4; s++) {
+                n.child[s] = BVH_EMPTY;
+                for (int k = 0; k < 3; k++) {
+                    n.lo[k][s] = std::numeric_limits<double>::infinity();
+                    n.hi[k][s] = -std::numeric_limits<double>::infinity();
+                }
+            }
+            for (int s = 0; s < 12; s++) n.pad[s] = 0;
+        }
+        uint32_t cut[5];
+        cut[0] = a;
+        cut[4] = b;
+        cut[2] = split(a, b);
+        cut[1] = (cut[2] - a > leaf_size) ? split(a, cut[2]) : a;          // a == "no split": slot 0 empty
+        cut[3] = (b - cut[2] > leaf_size) ? split(cut[2], b) : cut[2];
+        int slot = 0;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t qa = cut[q], qb = cut[q + 1];
+            if (qa == qb) continue;
+            const Box bx = bounds(qa, qb);
+            const uint32_t ref = (qb - qa <= leaf_size) ? make_leaf(qa, qb) : build_node(qa, qb, level + 1);
+            set_child(me, slot++, ref, bx);
+        }
+        return me;
+    }
+};
+
+}  // namespace
+
+bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
+                const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err) {
+    out = BvhBuild{};
+    if ((uint64_t)ns >= (1u << 30) || (uint64_t)nt >= (1u << 30) || (uint64_t)ns + nt >= (1u << 28)) {
+        err = "bvh: too many primitives";
+        return false;
+    }
+    // ---- leaf records ----
+    out.sph.resize(ns);
+    for (uint32_t i = 0; i < ns; i++) {
+        SphRec &s = out.sph[i];
+        s.c0x = sph[(size_t)SPH_C0X * ns + i]; s.c1x = sph[(size_t)SPH_C1X * ns + i];
+        s.c0y = sph[(size_t)SPH_C0Y * ns + i]; s.c1y = sph[(size_t)SPH_C1Y * ns + i];
+        s.c0z = sph[(size_t)SPH_C0Z * ns + i]; s.c1z = sph[(size_t)SPH_C1Z * ns + i];
+        s.cx = sph[(size_t)SPH_CX * ns + i]; s.cy = sph[(size_t)SPH_CY * ns + i]; s.cz = sph[(size_t)SPH_CZ * ns + i];
+        s.rr = sph[(size_t)SPH_RR * ns + i]; s.r = sph[(size_t)SPH_R * ns + i]; s.inv = sph[(size_t)SPH_INV * ns + i];
+        s.shape_id = sph_meta[i]; s.material = sph_meta[ns + i]; s.index = i; s.pad = 0;
+    }
+    out.tri.resize(nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        TriRec &q = out.tri[i];
+        q.v0x = tri[(size_t)TRI_V0X * nt + i]; q.v0y = tri[(size_t)TRI_V0Y * nt + i]; q.v0z = tri[(size_t)TRI_V0Z * nt + i];
+        q.e1x = tri[(size_t)TRI_E1X * nt + i]; q.e1y = tri[(size_t)TRI_E1Y * nt + i]; q.e1z = tri[(size_t)TRI_E1Z * nt + i];
+        q.e2x = tri[(size_t)TRI_E2X * nt + i]; q.e2y = tri[(size_t)TRI_E2Y * nt + i]; q.e2z = tri[(size_t)TRI_E2Z * nt + i];
+        q.shape_id = tri_meta[i]; q.material = tri_meta[nt + i]; q.index = i;
+        q.pad[0] = q.pad[1] = q.pad[2] = 0;
+    }
+    // ---- primitive boxes ----
+    Builder B;
+    B.out = &out;
+    B.items.reserve((size_t)ns + nt);
+    auto finite_box = [](const Box &b) {
+        for (int k = 0; k < 3; k++)
+            if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return false;
+        return true;
+    };
+    Box all;
+    all.reset();
+    for (uint32_t i = 0; i < ns; i++) {
+        Item it;
+        const SphRec &s = out.sph[i];
+        it.box.lo[0] = std::min(s.c0x, s.c1x); it.box.hi[0] = std::max(s.c0x, s.c1x);   // negative radii swap corners
+        it.box.lo[1] = std::min(s.c0y, s.c1y); it.box.hi[1] = std::max(s.c0y, s.c1y);
+        it.box.lo[2] = std::min(s.c0z, s.c1z); it.box.hi[2] = std::max(s.c0z, s.c1z);
+        it.ref = ((uint32_t)KIND_SPHERE << 30) | i;
+        if (!finite_box(it.box)) {  // NaN / inf geometry: keep the linear scan's verdict by testing it linearly
+            out.linear.push_back(i);
+            continue;
+        }
+        for (int k = 0; k < 3; k++) it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+        B.items.push_back(it);
+    }
+    for (uint32_t i = 0; i < nt; i++) {
+        Item it;
+        const TriRec &q = out.tri[i];
+        const double v0[3] = {q.v0x, q.v0y, q.v0z};
+        for (int k = 0; k < 3; k++) {
+            const double a = v0[k], b = tri_v1[3 * (size_t)i + k], c = tri_v2[3 * (size_t)i + k];
+            // the device works with e1 = v1 - v0, e2 = v2 - v0: cover both the given and the reconstructed vertices
+            const double e1 = (k == 0 ? q.e1x : k == 1 ? q.e1y : q.e1z), e2 = (k == 0 ? q.e2x : k == 1 ? q.e2y : q.e2z);
+            it.box.lo[k] = std::min({a, b, c, a + e1, a + e2});
+            it.box.hi[k] = std::max({a, b, c, a + e1, a + e2});
+            it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+        }
+        it.ref = ((uint32_t)KIND_TRI << 30) | i;
+        if (!finite_box(it.box)) {
+            err = "bvh: triangle " + std::to_string(i) + " has a non-finite vertex";
+            return false;
+        }
+        B.items.push_back(it);
+    }
+    // ---- oversized spheres go to the linear list (at most 64, largest first) ----
+    for (const Item &it : B.items) all.grow(it.box);
+    if (!B.items.empty()) {
+        // median-based scale so that one environment sphere does not define "large"
+        std::vector<double> diag;
+        diag.reserve(B.items.size());
+        auto diag_of = [](const Box &b) {
+            const double x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+            return std::sqrt(x * x + y * y + z * z);
+        };
+        Box cb;
+        cb.reset();
+        for (const Item &it : B.items) {
+            Box p;
+            for (int k = 0; k < 3; k++) p.lo[k] = p.hi[k] = it.c[k];
+            cb.grow(p);
+        }
+        // centroid bounds of everything but the largest 64 spheres approximate the populated region
+        std::vector<std::pair<double, size_t>> big;
+        for (size_t k = 0; k < B.items.size(); k++)
+            if ((B.items[k].ref >> 30) == KIND_SPHERE) big.push_back({diag_of(B.items[k].box), k});
+        std::sort(big.begin(), big.end(), [](auto &p, auto &q) { return p.first > q.first || (p.first == q.first && p.second < q.second); });
+        if (big.size() > 64) big.resize(64);
+        std::vector<char> drop(B.items.size(), 0);
+        if (B.items.size() > 64) {
+            std::vector<double> all_diag;
+            all_diag.reserve(B.items.size());
+            for (const Item &it : B.items) all_diag.push_back(diag_of(it.box));
+            std::nth_element(all_diag.begin(), all_diag.begin() + all_diag.size() / 2, all_diag.end());
+            const double median = all_diag[all_diag.size() / 2];
+            const double scene = diag_of(cb);
+            for (auto &p : big)
+                if (p.first > 0.25 * scene && p.first > 16.0 * median) drop[p.second] = 1;
+        }
+        std::vector<Item> kept;
+        kept.reserve(B.items.size());
+        for (size_t k = 0; k < B.items.size(); k++) {
+            if (drop[k]) out.linear.push_back(B.items[k].ref & 0x3FFFFFFFu);
+            else kept.push_back(B.items[k]);
+        }
+        B.items.swap(kept);
+    }
+    std::sort(out.linear.begin(), out.linear.end());
+    if (B.items.empty()) return true;  // tree-less: linear list only
+
+    all.reset();
+    for (const Item &it : B.items) all.grow(it.box);
+    double ext = 0.0;
+    for (int k = 0; k < 3; k++) ext = std::max({ext, std::fabs(all.lo[k]), std::fabs(all.hi[k])});
+    out.extent = ext;
+    B.pad = BVH_PAD_REL * std::max(ext, 1e-300);
+
+    // ---- leaf size: smallest in {4, 8} whose (balanced) tree fits the traversal stack ----
+    const uint64_t n = B.items.size();
+    const std::vector<Item> pristine = B.items;
+    for (uint32_t leaf = 4;; leaf *= 2) {
+        if (leaf > 8) {
+            err = "bvh: tree depth " + std::to_string(out.depth) + " exceeds the traversal stack (scene too large)";
+            return false;
+        }
+        B.items = pristine;
+        B.leaf_size = leaf;
+        out.leaf_size = leaf;
+        out.nodes.clear();
+        out.prims.clear();
+        out.depth = 0;
+        out.nodes.reserve(n / 2 + 16);
+        out.prims.reserve(n);
+        if (n <= leaf) {  // a single leaf under a root node
+            out.nodes.emplace_back();
+            BvhNode4 &r = out.nodes[0];
+            for (int s = 0; s < 4; s++) {
+                r.child[s] = BVH_EMPTY;
+                for (int k = 0; k < 3; k++) r.lo[k][s] = std::numeric_limits<double>::infinity(), r.hi[k][s] = -r.lo[k][s];
+            }
+            for (int s = 0; s < 12; s++) r.pad[s] = 0;
+            out.depth = 1;
+            B.set_child(0, 0, B.make_leaf(0, (uint32_t)n), B.bounds(0, (uint32_t)n));
+        } else {
+            B.build_node(0, (uint32_t)n, 0);
+        }
+        if (3 * out.depth + 1 <= BVH_STACK) break;
+    }
+    return true;
+}

@@ -1,0 +1,244 @@
+// flux_bvh.cuh — EXTENSION: 4-wide bounding-volume hierarchy over sphere and triangle
+// boxes, and its closest-hit traversal.  The reference has no acceleration structure: Scene::hit is a
+// linear scan (fluxcore/src/scene.rs:156-160).  The contract of this file is therefore "return exactly
+// what the linear scan returns" — same shape id (ties to the lower id, common.rs:17-23) and the same
+// bits of t — only faster for scenes with thousands to millions of shapes.
+//
+// Why the result is identical:
+//   * primitives reached in a leaf are tested by the very same device functions as the linear scan
+//     (sphere_t = BoundingBox::hit + quadratic, tri_t) and folded with the order-independent consider();
+//   * a node may be skipped only if no primitive below it can yield a candidate.  Node boxes are unions
+//     of the primitive boxes (spheres: centre -+ r exactly as Sphere::new, shapes.rs:154-169; triangles:
+//     vertex min/max) grown by BVH_PAD_REL * scene extent.  The slab expression (c - o) * (1/d) is the
+//     one BoundingBox::hit uses and is monotone in c under IEEE rounding, so a box that contains a
+//     primitive box passes whenever the primitive's own test passes; NaN slabs (0 * inf) never cull
+//     (fmax/fmin ignore NaN, the comparisons below are false for NaN);
+//   * distance pruning compares the node's entry distance with t_best plus a margin of 1e-9 relative
+//     (seven orders of magnitude above the rounding difference between a quadratic root and a slab
+//     entry), so a root that rounds to just in front of its own box is never lost.
+// Planes are unbounded and a few very large spheres (environment spheres) would bloat the top of the
+// tree: both are kept in a linear list that is tested before the traversal.
+//
+// Layout: BvhNode4 is 256 B (two 128 B lines), child boxes SoA so that one double2 load serves two
+// children; a child reference is an inner node index, a leaf (offset, count) into bvh_prims, or EMPTY.
+// Leaf primitives are fetched from 128 B / 80 B array-of-structure records (one or two lines per
+// primitive) instead of the 12 strided planes of the linear-scan SoA.
+#pragma once
+#include "flux_intersect.cuh"
+
+#define BVH_EMPTY 0xFFFFFFFFu
+#define BVH_LEAF 0x80000000u
+#define BVH_STACK 32          // entries per thread (shared memory); the builder keeps 3*depth+1 below it
+#define BVH_PAD_REL 1e-7
+#define BVH_PRUNE_REL 1e-9
+
+struct __align__(256) BvhNode4 {
+    double lo[3][4];     // [axis][child]
+    double hi[3][4];
+    uint32_t child[4];   // EMPTY | inner node index | LEAF | offset << 3 | (count - 1)
+    uint32_t pad[12];
+};
+static_assert(sizeof(BvhNode4) == 256, "BvhNode4 layout");
+
+// leaf records
+struct __align__(16) SphRec {   // 112 B
+    double c0x, c1x, c0y, c1y, c0z, c1z;   // bounding box, shapes.rs:156-161
+    double cx, cy, cz, rr;
+    double r, inv;
+    uint32_t shape_id, material, index, pad;
+};
+struct __align__(16) TriRec {   // 80 B... padded to 96
+    double v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+    uint32_t shape_id, material;
+    uint32_t index, pad[3];
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// Sphere::hit distance on a leaf record (same expressions as sphere_t in flux_intersect.cuh).
+template <bool COUNT>
+__device__ __forceinline__ bool sphere_t_rec(const RayCtx &r, const SphRec *__restrict__ s, double &t_out,
+                                             unsigned long long *cn) {
+    if (COUNT) cn[CN_BBOX_TESTS]++;
+    const double2 bx = ldg2(&s->c0x), by = ldg2(&s->c0y), bz = ldg2(&s->c0z);
+    if (!bbox_hit(r, bx.x, by.x, bz.x, bx.y, by.y, bz.y)) return false;
+    if (COUNT) cn[CN_BBOX_PASS]++;
+    const double2 c01 = ldg2(&s->cx), c23 = ldg2(&s->cz);
+    V3 temp = r.o - mk3(c01.x, c01.y, c23.x);
+    double b = 2.0 * dot3(temp, r.d);
+    double cc = dot3(temp, temp) - c23.y;
+    double disc = b * b - r.A4 * cc;
+    if (disc < 0.0) return false;
+    if (COUNT) cn[CN_DISC_NONNEG]++;
+    double e = sqrt(disc);
+    double t = (-b - e) / r.A2;
+    if (!(t > FLUX_T_MIN)) {
+        if (COUNT) cn[CN_T2]++;
+        t = (-b + e) / r.A2;
+        if (!(t > FLUX_T_MIN)) return false;
+    }
+    t_out = t;
+    return true;
+}
+
+__device__ __forceinline__ bool tri_t_rec(const RayCtx &r, const TriRec *__restrict__ q, double &t_out) {
+    const double2 a = ldg2(&q->v0x), b = ldg2(&q->v0z), c = ldg2(&q->e1y), d = ldg2(&q->e2x);
+    const double e2z = __ldg(&q->e2z);
+    const V3 v0 = mk3(a.x, a.y, b.x), e1 = mk3(b.y, c.x, c.y), e2 = mk3(d.x, d.y, e2z);
+    V3 p = cross3(r.d, e2);
+    double det = dot3(e1, p);
+    if (det == 0.0) return false;
+    double inv = 1.0 / det;
+    V3 s = r.o - v0;
+    double u = dot3(s, p) * inv;
+    if (!(u >= 0.0 && u <= 1.0)) return false;
+    V3 qv = cross3(s, e1);
+    double v = dot3(r.d, qv) * inv;
+    if (!(v >= 0.0 && u + v <= 1.0)) return false;
+    double t = dot3(e2, qv) * inv;
+    if (!(t > FLUX_T_MIN)) return false;
+    t_out = t;
+    return true;
+}
+
+// Scene::hit through the BVH.  `stack` points at this thread's column of a [BVH_STACK][blockDim.x] uint2
+// array in shared memory (entry e of thread t at stack[e * stride]).
+template <bool COUNT>
+__device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayCtx &r, uint2 *stack, uint32_t stride,
+                                                  unsigned long long *cn) {
+    HitRef best;
+    best.t = 0.0;
+    best.shape_id = 0xFFFFFFFFu;
+    best.kind = 0;
+    best.index = 0;
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k|
+    const double tscale = sc.bvh_extent * fmin(fabs(r.ia), fmin(fabs(r.ib), fabs(r.ic)));
+    double t_prune = inf;
+#define BVH_CONSIDER(T, ID, KIND, INDEX)                                               \
+    do {                                                                               \
+        if (COUNT) cn[CN_CANDIDATES]++;                                                \
+        consider(best, (T), (ID), (KIND), (INDEX));                                    \
+        t_prune = best.t + BVH_PRUNE_REL * (fabs(best.t) + tscale);                    \
+    } while (0)
+
+    // ---- unbounded / oversized shapes: linear, first (they tighten t_prune early) ----
+    for (uint32_t i = 0; i < sc.n_planes; i++) {
+        double t;
+        if (COUNT) cn[CN_PLANE_TESTS]++;
+        if (plane_t(r, sc.pln, sc.n_planes, i, t)) BVH_CONSIDER(t, __ldg(sc.pln_meta + i), KIND_PLANE, i);
+    }
+    for (uint32_t k = 0; k < sc.bvh_n_linear; k++) {
+        const uint32_t i = __ldg(sc.bvh_linear + k);
+        double t;
+        if (sphere_t<COUNT>(r, sc.sph, sc.n_spheres, i, t, cn)) BVH_CONSIDER(t, __ldg(sc.sph_meta + i), KIND_SPHERE, i);
+    }
+    if (sc.bvh_n_nodes == 0) return best;
+
+    const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
+    const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
+    const TriRec *__restrict__ trec = reinterpret_cast<const TriRec *>(sc.bvh_tri);
+    uint32_t sp = 0;
+    uint32_t cur = 0;  // root
+    for (;;) {
+        if (!(cur & BVH_LEAF)) {
+            if (COUNT) cn[CN_NODES]++;
+            const BvhNode4 *nd = nodes + cur;
+            // near/far corner per axis by the sign test of BoundingBox::hit (shapes.rs:108,115,122)
+            const double *nx = r.pa ? nd->lo[0] : nd->hi[0], *fx = r.pa ? nd->hi[0] : nd->lo[0];
+            const double *ny = r.pb ? nd->lo[1] : nd->hi[1], *fy = r.pb ? nd->hi[1] : nd->lo[1];
+            const double *nz = r.pc ? nd->lo[2] : nd->hi[2], *fz = r.pc ? nd->hi[2] : nd->lo[2];
+            const uint4 ch = __ldg(reinterpret_cast<const uint4 *>(nd->child));
+            double t0[4];
+            uint32_t ref[4];
+            ref[0] = ch.x; ref[1] = ch.y; ref[2] = ch.z; ref[3] = ch.w;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const double2 ax = ldg2(nx + 2 * h), bx = ldg2(fx + 2 * h);
+                const double2 ay = ldg2(ny + 2 * h), by = ldg2(fy + 2 * h);
+                const double2 az = ldg2(nz + 2 * h), bz = ldg2(fz + 2 * h);
+                {
+                    const double tn = fmax(fmax((ax.x - r.o.x) * r.ia, (ay.x - r.o.y) * r.ib), (az.x - r.o.z) * r.ic);
+                    const double tf = fmin(fmin((bx.x - r.o.x) * r.ia, (by.x - r.o.y) * r.ib), (bz.x - r.o.z) * r.ic);
+                    const bool skip = (tn >= tf) || (tf <= FLUX_T_MIN) || (tn > t_prune);
+                    t0[2 * h] = tn;
+                    if (skip) ref[2 * h] = BVH_EMPTY;
+                }
+                {
+                    const double tn = fmax(fmax((ax.y - r.o.x) * r.ia, (ay.y - r.o.y) * r.ib), (az.y - r.o.z) * r.ic);
+                    const double tf = fmin(fmin((bx.y - r.o.x) * r.ia, (by.y - r.o.y) * r.ib), (bz.y - r.o.z) * r.ic);
+                    const bool skip = (tn >= tf) || (tf <= FLUX_T_MIN) || (tn > t_prune);
+                    t0[2 * h + 1] = tn;
+                    if (skip) ref[2 * h + 1] = BVH_EMPTY;
+                }
+            }
+            // order: EMPTY last, then by entry distance (NaN entry = unknown = nearest); 5-comparator network
+#define BVH_KEY(k) (ref[k] == BVH_EMPTY ? inf : (t0[k] == t0[k] ? t0[k] : -inf))
+            double key[4] = {BVH_KEY(0), BVH_KEY(1), BVH_KEY(2), BVH_KEY(3)};
+#define BVH_CSWAP(a, b)                                                         \
+    if (key[b] < key[a]) {                                                      \
+        const double tk = key[a]; key[a] = key[b]; key[b] = tk;                 \
+        const uint32_t tr = ref[a]; ref[a] = ref[b]; ref[b] = tr;               \
+    }
+            BVH_CSWAP(0, 1) BVH_CSWAP(2, 3) BVH_CSWAP(0, 2) BVH_CSWAP(1, 3) BVH_CSWAP(1, 2)
+#undef BVH_CSWAP
+#undef BVH_KEY
+            // push far children first so that the nearest is popped first; continue with the nearest
+#pragma unroll
+            for (int k = 3; k >= 1; k--)
+                if (ref[k] != BVH_EMPTY) {
+                    // entry distance rounded DOWN to f32: a conservative re-test when popped
+                    stack[(size_t)sp * stride] = make_uint2(ref[k], __float_as_uint(__double2float_rd(key[k])));
+                    sp++;
+                }
+            if (ref[0] != BVH_EMPTY) {
+                cur = ref[0];
+                continue;
+            }
+        } else {
+            const uint32_t off = (cur & 0x7FFFFFFFu) >> 3, cnt = (cur & 7u) + 1u;
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t pr = __ldg(sc.bvh_prims + off + k);
+                const uint32_t idx = pr & 0x3FFFFFFFu;
+                double t;
+                if ((pr >> 30) == KIND_SPHERE) {
+                    const SphRec *s = srec + idx;
+                    if (sphere_t_rec<COUNT>(r, s, t, cn)) BVH_CONSIDER(t, __ldg(&s->shape_id), KIND_SPHERE, idx);
+                } else {
+                    const TriRec *q = trec + idx;
+                    if (COUNT) cn[CN_TRI_TESTS]++;
+                    if (tri_t_rec(r, q, t)) BVH_CONSIDER(t, __ldg(&q->shape_id), KIND_TRI, idx);
+                }
+            }
+        }
+        // pop
+        for (;;) {
+            if (sp == 0) return best;
+            sp--;
+            const uint2 e = stack[(size_t)sp * stride];
+            if ((double)__uint_as_float(e.y) > t_prune) continue;  // became prunable since it was pushed
+            cur = e.x;
+            break;
+        }
+    }
+#undef BVH_CONSIDER
+}
+#endif  // __CUDACC__
+
+// ---- host builder (bvh_build.cu) ----
+#include <string>
+#include <vector>
+struct BvhBuild {
+    std::vector<BvhNode4> nodes;
+    std::vector<uint32_t> prims;     // (kind << 30) | index, in leaf order
+    std::vector<uint32_t> linear;    // sphere indices kept out of the tree
+    std::vector<SphRec> sph;         // [n_spheres], indexed like the SoA arrays
+    std::vector<TriRec> tri;         // [n_triangles]
+    double extent = 0.0;             // max |coordinate| over the boxes in the tree
+    uint32_t depth = 0;              // levels of 4-wide nodes
+    uint32_t leaf_size = 0;
+};
+// sph: SoA [SPH_FIELDS][ns] as uploaded; tri: SoA [TRI_FIELDS][nt]; v1/v2: original vertices (for the boxes)
+bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
+                const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err);

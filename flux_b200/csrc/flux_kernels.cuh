@@ -3,6 +3,7 @@
 #include "flux_scene.cuh"
 
 #define FLUX_MAX_DEPTH_CAP 32  // per-path (f, weight) stack entries
+#define FLUX_LINEAR_LIMIT 64   // bounded shapes (spheres + triangles) up to which closest-hit scans linearly
 
 // Camera::render for a list of rows (trace.rs:53-97).
 void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);

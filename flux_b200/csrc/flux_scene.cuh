@@ -48,11 +48,16 @@ struct DevScene {
     const double *tri;
     const uint32_t *tri_meta;
     const DevMaterial *materials;
-    // BVH over sphere/triangle boxes (extension; null when linear scan is used)
-    const void *bvh_nodes;
+    // BVH over sphere/triangle boxes (EXTENSION, flux_bvh.cuh; unused when the linear scan is selected)
+    const void *bvh_nodes;      // BvhNode4[bvh_n_nodes]
     const uint32_t *bvh_prims;  // leaf primitive refs: (kind<<30 | index)
+    const void *bvh_sph;        // SphRec[n_spheres]
+    const void *bvh_tri;        // TriRec[n_tris]
+    const uint32_t *bvh_linear; // spheres kept out of the tree (oversized / non-finite), ascending
+    uint32_t bvh_n_linear;
     uint32_t bvh_n_nodes;
     uint32_t use_bvh;
+    double bvh_extent;          // max |coordinate| of the boxes in the tree (scale of the pruning margin)
 };
 
 struct DevSamples {

@@ -11,6 +11,7 @@
 // pixel; lane g takes samples g, g+G, ...; the per-pixel sum is a fixed-shape
 // xor-shuffle tree, so the result does not depend on grid size, scheduling or
 // the number of GPUs.
+#include "flux_bvh.cuh"
 #include "flux_intersect.cuh"
 #include "flux_kernels.cuh"
 #include "flux_shade.cuh"
@@ -33,9 +34,9 @@ __device__ __forceinline__ void primary_ray(const DevCamera &cam, uint32_t row, 
 }
 
 // scene.shade(&r, 1, ..) for one camera sample.
-template <bool COUNT>
+template <bool COUNT, bool BVH>
 __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uint32_t set, uint32_t i, double2 ps,
-                                          unsigned long long *cn) {
+                                          uint2 *stack, unsigned long long *cn) {
     double sf[FLUX_MAX_DEPTH_CAP][4];  // (f.r, f.g, f.b, weight) per bounce
     uint32_t top = 0;
     Rgb L;
@@ -49,7 +50,7 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
         }
         if (COUNT) cn[CN_SEGMENTS]++;
         RayCtx r = make_ray(o, d);
-        HitRef h = closest_hit_linear<COUNT>(sc, r, cn);
+        HitRef h = BVH ? closest_hit_bvh<COUNT>(sc, r, stack, blockDim.x, cn) : closest_hit_linear<COUNT>(sc, r, cn);
         if (h.shape_id == 0xFFFFFFFFu) {  // scene.rs:168
             if (COUNT) cn[CN_MISS]++;
             L = Rgb{p.cam.bg[0], p.cam.bg[1], p.cam.bg[2]};
@@ -105,8 +106,10 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
     return L;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ RenderParams p, uint32_t G) {
+    extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x] when BVH
+    uint2 *stack = BVH ? bvh_stack + threadIdx.x : nullptr;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ppw = 32u / G;  // pixels per warp
     const uint32_t g = lane % G;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
                 V3 o, d;
                 primary_ray(p.cam, row, col, s, l, o, d);
                 if (COUNT) cn[CN_SAMPLES]++;
-                Rgb c = trace_path<COUNT>(p, o, d, set, i, s, cn);
+                Rgb c = trace_path<COUNT, BVH>(p, o, d, set, i, s, stack, cn);
                 acc.r += c.r;
                 acc.g += c.g;
                 acc.b += c.b;
@@ -189,19 +192,31 @@ void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t
     uint64_t want = (n_items + (threads / 32) - 1) / (threads / 32);
     uint64_t cap = (uint64_t)sm_count * 4;
     int blocks = (int)(want < cap ? (want ? want : 1) : cap);
-    if (count)
-        render_kernel<true><<<blocks, threads, 0, stream>>>(p, G);
-    else
-        render_kernel<false><<<blocks, threads, 0, stream>>>(p, G);
+    const bool bvh = p.scene.use_bvh != 0;
+    const size_t smem = bvh ? (size_t)BVH_STACK * threads * sizeof(uint2) : 0;
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, threads, smem, stream>>>(p, G);
+    };
+    if (count) {
+        if (bvh) go(render_kernel<true, true>);
+        else go(render_kernel<true, false>);
+    } else {
+        if (bvh) go(render_kernel<false, true>);
+        else go(render_kernel<false, false>);
+    }
 }
 
 // ---- Scene::hit on an explicit ray batch (K6) -------------------------------
-__global__ void __launch_bounds__(256) trace_rays_kernel(const __grid_constant__ DevScene sc, uint64_t n,
+template <bool BVH>
+__global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__ DevScene sc, uint64_t n,
                                                          const double *__restrict__ o, const double *__restrict__ d,
                                                          int32_t *__restrict__ hit, double *__restrict__ t) {
+    extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x] when BVH
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         RayCtx r = make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
-        HitRef h = closest_hit_linear<false>(sc, r, nullptr);
+        HitRef h = BVH ? closest_hit_bvh<false>(sc, r, bvh_stack + threadIdx.x, blockDim.x, nullptr)
+                       : closest_hit_linear<false>(sc, r, nullptr);
         if (h.shape_id == 0xFFFFFFFFu) {
             hit[i] = -1;
             t[i] = __longlong_as_double(0x7FF0000000000000ll);
@@ -215,9 +230,17 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(const __grid_constant__
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
                        int sm_count, cudaStream_t stream) {
     if (n == 0) return;
-    const int threads = 256;
+    const int threads = 128;
     uint64_t want = (n + threads - 1) / threads;
-    uint64_t cap = (uint64_t)sm_count * 8;
-    int blocks = (int)(want < cap ? want : cap);
-    trace_rays_kernel<<<blocks, threads, 0, stream>>>(sc, n, o, d, hit, t);
+    if (sc.use_bvh) {
+        // one ray per thread: traversal lengths vary a lot, so let the hardware scheduler balance the CTAs
+        const size_t smem = (size_t)BVH_STACK * threads * sizeof(uint2);
+        uint64_t cap = 0x7FFFFFFFull;
+        int blocks = (int)(want < cap ? want : cap);
+        trace_rays_kernel<true><<<blocks, threads, smem, stream>>>(sc, n, o, d, hit, t);
+    } else {
+        uint64_t cap = (uint64_t)sm_count * 16;
+        int blocks = (int)(want < cap ? want : cap);
+        trace_rays_kernel<false><<<blocks, threads, 0, stream>>>(sc, n, o, d, hit, t);
+    }
 }

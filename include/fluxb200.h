@@ -240,6 +240,14 @@ int flux_launch_count(flux_ctx *ctx, uint64_t *n);
  * 2 = BVH.  Results are identical by construction; used by parity tests. */
 int flux_set_accel_mode(flux_ctx *ctx, int mode);
 
+/* Host-only description of the acceleration structure flux_set_scene would build for `scene` (EXTENSION;
+ * needs no device, so the builder is testable on CPU).  Builds the BVH, checks that every primitive box lies
+ * inside the box of the leaf slot that holds it and every child box inside its parent slot, and reports:
+ * out[0] nodes, out[1] 4-wide levels, out[2] leaf size, out[3] shapes on the linear list, out[4] primitive
+ * references in the tree, out[5] containment violations (must be 0), out[6] primitives referenced more or less
+ * than once (must be 0), out[7] 1 if flux_set_scene would use the BVH in auto mode else 0. */
+int flux_bvh_describe(const flux_scene_flat *scene, uint64_t out[8]);
+
 /* Force the render kernel variant: 0 = auto, 1 = direct (lane group per pixel), 2 = regeneration
  * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene),
  * 3 = block-local wavefront (CTA per pixel, compacted candidate pairs, material-sorted shading;

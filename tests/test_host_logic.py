@@ -113,3 +113,45 @@ def test_ops_model_matches_survey_magnitude(demo2):
     assert cn["segments"] == cn["emissive"] + cn["matte"] + cn["glossy"] + cn["specular"] + cn["miss"]
     assert cn["hit_sphere"] + cn["hit_plane"] + cn["miss"] == cn["segments"]
     assert set(_capi.COUNTER_FIELDS) == set(cn)
+
+
+# ---- BVH builder (EXTENSION; host code inside libfluxb200.so, no device needed) ----
+def _describe(flat):
+    import ctypes
+    from flux_b200 import _capi
+    out = (ctypes.c_uint64 * 8)()
+    assert _capi.lib().flux_bvh_describe(flat.ptr(), out) == 0
+    return dict(zip(("nodes", "levels", "leaf", "linear", "refs", "violations", "miscount", "auto"), list(out)))
+
+
+def test_bvh_builder_invariants_sphere_cloud():
+    from flux_b200 import synth
+    flat = synth.sphere_cloud_scene(10_000, seed=5).flatten()
+    d = _describe(flat)
+    assert d["violations"] == 0 and d["miscount"] == 0
+    assert d["refs"] + d["linear"] == 10_000 and d["linear"] == 0
+    assert d["auto"] == 1 and 3 * d["levels"] + 1 <= 32 and d["leaf"] == 4
+    assert d["nodes"] < 10_000 // 2
+
+
+def test_bvh_builder_keeps_oversized_spheres_linear_and_handles_meshes():
+    from flux_b200 import synth
+    flat = synth.mesh_scene(100, 60, seed=3, width=64, height=48).flatten()
+    d = _describe(flat)
+    assert d["violations"] == 0 and d["miscount"] == 0
+    assert d["linear"] == 2 and d["refs"] == 2 * 100 * 60      # environment sphere + light stay out of the tree
+    assert d["auto"] == 1
+
+
+def test_bvh_builder_small_and_degenerate_scenes(demo2):
+    d = _describe(demo2.flatten())
+    assert d["violations"] == 0 and d["miscount"] == 0 and d["auto"] == 0   # 12 spheres: linear scan in auto mode
+    from flux_b200.scene import SceneData, SphereData, Matte
+    m = Matte((0.5, 0.5, 0.5), (1, 1, 1), 1.0)
+    same = [SphereData((1.0, 2.0, 3.0), 0.5, m, False) for _ in range(200)]   # identical centroids: median split must terminate
+    sd = SceneData("same", demo2.output_settings, (0, 0, 0), same, demo2.camera_settings, demo2.camera_data)
+    d = _describe(sd.flatten())
+    assert d["violations"] == 0 and d["miscount"] == 0 and d["refs"] == 200
+    one = SceneData("one", demo2.output_settings, (0, 0, 0), same[:1], demo2.camera_settings, demo2.camera_data)
+    d = _describe(one.flatten())
+    assert d["nodes"] == 1 and d["refs"] == 1 and d["miscount"] == 0
