@@ -8,9 +8,9 @@ without a CUDA device raises.
 """
 from .scene import (CameraData, CameraSettings, Emissive, GlossyReflective, JobConfiguration, Matte,
                     MeshData, OutputSettings, PlaneData, Reflective, SceneData, SphereData,
-                    TriangleData, WorkUnit, WorkUnitResult, work_units)
+                    TriangleData, RectangleData, BoxData, WorkUnit, WorkUnitResult, work_units)
 
 __all__ = ["CameraData", "CameraSettings", "Emissive", "GlossyReflective", "JobConfiguration", "Matte",
            "MeshData", "OutputSettings", "PlaneData", "Reflective", "SceneData", "SphereData",
-           "TriangleData", "WorkUnit", "WorkUnitResult", "work_units"]
+           "TriangleData", "RectangleData", "BoxData", "WorkUnit", "WorkUnitResult", "work_units"]
 __version__ = "0.1.0"

@@ -144,7 +144,43 @@ class MeshData:  # EXTENSION: many triangles sharing one material
     material: MaterialData
 
 
-ShapeData = Union[SphereData, PlaneData, TriangleData, MeshData]
+@dataclass(frozen=True)
+class RectangleData:  # EXTENSION (TODO.md:2 "Quad (for area light)"): corner + two edge vectors, two triangles
+    corner: tuple
+    edge_a: tuple
+    edge_b: tuple
+    material: MaterialData
+
+    def triangles(self):
+        """(v0, v1, v2) triples; both wound so that the normal is edge_a x edge_b."""
+        c = np.asarray(self.corner, np.float64)
+        pa = c + np.asarray(self.edge_a, np.float64)
+        pab = pa + np.asarray(self.edge_b, np.float64)
+        pb = c + np.asarray(self.edge_b, np.float64)
+        return [(c, pa, pab), (c, pab, pb)]
+
+
+@dataclass(frozen=True)
+class BoxData:  # EXTENSION: axis-aligned box [min, max], six outward-facing rectangles = twelve triangles
+    min: tuple
+    max: tuple
+    material: MaterialData
+
+    def rectangles(self):
+        (x0, y0, z0), (x1, y1, z1) = self.min, self.max
+        dx, dy, dz = x1 - x0, y1 - y0, z1 - z0
+        m = self.material
+        return [
+            RectangleData((x0, y0, z0), (0.0, dy, 0.0), (dx, 0.0, 0.0), m),   # z = z0, normal -z
+            RectangleData((x0, y0, z1), (dx, 0.0, 0.0), (0.0, dy, 0.0), m),   # z = z1, normal +z
+            RectangleData((x0, y0, z0), (0.0, 0.0, dz), (0.0, dy, 0.0), m),   # x = x0, normal -x
+            RectangleData((x1, y0, z0), (0.0, dy, 0.0), (0.0, 0.0, dz), m),   # x = x1, normal +x
+            RectangleData((x0, y0, z0), (dx, 0.0, 0.0), (0.0, 0.0, dz), m),   # y = y0, normal -y
+            RectangleData((x0, y1, z0), (0.0, 0.0, dz), (dx, 0.0, 0.0), m),   # y = y1, normal +y
+        ]
+
+
+ShapeData = Union[SphereData, PlaneData, TriangleData, MeshData, RectangleData, BoxData]
 
 
 def shape_from_yaml(d) -> ShapeData:
@@ -167,6 +203,12 @@ def shape_from_yaml(d) -> ShapeData:
         v = np.asarray(_req(s, "vertices", tag), dtype=np.float64).reshape(-1, 3)
         f = np.asarray(_req(s, "faces", tag), dtype=np.int64).reshape(-1, 3)
         return MeshData(v, f, material_from_yaml(_req(s, "material", tag)))
+    if tag == "Rectangle":  # EXTENSION
+        return RectangleData(_vec3(_req(s, "corner", tag), "corner"), _vec3(_req(s, "edge_a", tag), "edge_a"),
+                             _vec3(_req(s, "edge_b", tag), "edge_b"), material_from_yaml(_req(s, "material", tag)))
+    if tag == "Box":  # EXTENSION
+        return BoxData(_vec3(_req(s, "min", tag), "min"), _vec3(_req(s, "max", tag), "max"),
+                       material_from_yaml(_req(s, "material", tag)))
     raise ValueError(f"unknown variant `{tag}`, expected `Sphere` or `Plane`")
 
 
@@ -320,6 +362,14 @@ class SceneData:  # scene.rs:42-49
                 t2.append(np.asarray([sh.v2], np.float64))
                 tid.append(np.asarray([shape_id], np.uint32)); tm.append(np.asarray([mat_id(sh.material)], np.uint32))
                 shape_id += 1
+            elif isinstance(sh, (RectangleData, BoxData)):
+                rects = [sh] if isinstance(sh, RectangleData) else sh.rectangles()
+                for rc in rects:
+                    for (a, b, c) in rc.triangles():
+                        t0.append(np.asarray([a], np.float64)); t1.append(np.asarray([b], np.float64))
+                        t2.append(np.asarray([c], np.float64))
+                        tid.append(np.asarray([shape_id], np.uint32)); tm.append(np.asarray([mat_id(rc.material)], np.uint32))
+                        shape_id += 1
             elif isinstance(sh, MeshData):
                 f = np.asarray(sh.faces, dtype=np.int64)
                 v = np.asarray(sh.vertices, dtype=np.float64)

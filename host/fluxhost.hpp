@@ -1,0 +1,169 @@
+// fluxhost.hpp — C++17 host side above the C-ABI of include/fluxb200.h.
+//
+// The reference's host is Rust (fluxcore + the flux binary); this image has no Rust toolchain, so the host
+// that is built and tested here is C++ and mirrors the reference's interface for the render path by name
+// and meaning:
+//
+//   fluxcore/src/scene.rs:42-74    SceneData, OutputSettings, CameraSettings, CameraData, ShapeData
+//   fluxcore/src/shapes.rs:18-83   SphereData, PlaneData, MaterialData::{Matte,Emissive,Reflective,GlossyReflective}
+//   fluxcore/src/job.rs:40-88      JobConfiguration, WorkUnit, Job::work_units
+//   fluxcore/src/manager.rs:25-33  WorkUnitResult, WorkerInfo;  :232-236 trait Worker -> GpuWorker
+//   fluxcore/src/workers.rs:46-64  the LocalWorker loop body   -> GpuWorker::run_job
+//   fluxcore/src/trace.rs:26,53    Camera::new, Camera::render
+//   fluxcore/src/image.rs:5-60     Image, Image::write (P3 PPM, maxval 65535)
+//   flux/src/main.rs:28-29         serde_yaml::from_reader     -> SceneData::from_yaml_file
+//
+// Triangle / Mesh / Rectangle / Box are EXTENSIONS of ShapeData (the reference has Sphere and Plane only).
+// Everything that computes pixels is behind libfluxb200.so; there is no CPU rendering path in this file.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <variant>
+#include <vector>
+
+#include "../include/fluxb200.h"
+
+namespace flux {
+
+using Vec3 = std::array<double, 3>;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- MaterialData, shapes.rs:42-83 ----
+struct MatteData { Vec3 diffuse_color, ambient_color; double diffuse_coefficient; };
+struct EmissiveData { Vec3 color; double power; };
+struct ReflectiveData { double reflect_amount; Vec3 reflect_color; };
+struct GlossyReflectiveData { double reflect_amount; Vec3 reflect_color; double reflect_exponent; };
+using MaterialData = std::variant<MatteData, EmissiveData, ReflectiveData, GlossyReflectiveData>;
+
+// ---- ShapeData, scene.rs:71-74 + shapes.rs:18-37 (+ extensions) ----
+struct SphereData { Vec3 center; double radius; MaterialData material; bool invert; };
+struct PlaneData { Vec3 point, normal; MaterialData material; };
+struct TriangleData { Vec3 v0, v1, v2; MaterialData material; };                                    // EXTENSION
+struct MeshData { std::vector<Vec3> vertices; std::vector<std::array<int64_t, 3>> faces; MaterialData material; };  // EXTENSION
+struct RectangleData { Vec3 corner, edge_a, edge_b; MaterialData material; };                       // EXTENSION
+struct BoxData { Vec3 min, max; MaterialData material; };                                           // EXTENSION
+using ShapeData = std::variant<SphereData, PlaneData, TriangleData, MeshData, RectangleData, BoxData>;
+
+struct OutputSettings { uint32_t image_width, image_height; double pixel_size; };   // scene.rs:58-63
+struct CameraSettings { Vec3 eye, look_at, up; };                                  // scene.rs:11-16
+struct CameraData { double zoom_factor, view_plane_distance, focal_distance, lens_radius; };  // scene.rs:50-56
+
+struct JobConfiguration {          // job.rs:49-53; defaults flux/src/main.rs:20-21,172
+    uint32_t sample_root = 1;
+    uint32_t max_trace_depth = 5;
+    uint32_t rows_per_work_unit = 50;
+};
+
+struct WorkUnit { uint32_t row_start, row_end; uint64_t job_id; };   // job.rs:40-44, row_end inclusive
+struct WorkUnitResult {                                             // manager.rs:25-28
+    WorkUnit work_unit;
+    std::vector<double> rows;   // [row_end-row_start+1][W][3], linear RGB, averaged and max_to_one-clamped
+};
+struct WorkerInfo { std::string name; uint32_t num_threads; };      // manager.rs:30-33
+
+// Owns the arrays a flux_scene_flat points into.
+struct FlatScene {
+    flux_scene_flat flat{};
+    std::vector<flux_material> materials;
+    std::vector<double> sphere_center, sphere_radius, plane_point, plane_normal, tri_v0, tri_v1, tri_v2;
+    std::vector<uint8_t> sphere_invert;
+    std::vector<uint32_t> sphere_shape_id, sphere_material, plane_shape_id, plane_material, tri_shape_id, tri_material;
+    uint32_t n_shapes = 0;
+    const flux_scene_flat *ptr();
+};
+
+struct SceneData {   // scene.rs:42-49
+    std::string scene_name;
+    OutputSettings output_settings{};
+    Vec3 background{};
+    std::vector<ShapeData> shapes;
+    CameraSettings camera_settings{};
+    CameraData camera_data{};
+
+    // serde_yaml::from_reader (flux/src/main.rs:28-29): every field required, unknown keys ignored,
+    // anchors/aliases resolved, Vector3/Point3/Color accepted as 3-element sequences.
+    static SceneData from_yaml_file(const std::string &path);
+    static SceneData from_yaml_string(const std::string &text);
+    SceneData with_size(uint32_t width, uint32_t height) const;   // BASELINE config 1 (no CLI override in the reference)
+    // plain data -> per-kind arrays with one shared shape-id space (include/fluxb200.h flux_scene_flat)
+    std::unique_ptr<FlatScene> flatten() const;
+};
+
+// Job::work_units (job.rs:66-88) without its dropped-trailing-row quirk: covers every row.
+std::vector<WorkUnit> work_units(uint32_t image_height, uint32_t rows_per_work_unit, uint64_t job_id = 0);
+
+// Image, image.rs:5-60.
+struct Image {
+    uint32_t width = 0, height = 0;
+    std::vector<double> pixels;   // [H][W][3]; rows never set stay black (image.rs:54-58)
+    Image(uint32_t w, uint32_t h) : width(w), height(h), pixels((size_t)w * h * 3, 0.0) {}
+    void set_rows(const WorkUnitResult &r);          // ImageBuilder: manager.rs:316-325
+    void write(const std::string &path) const;       // image.rs:42-60 via flux_write_ppm
+};
+
+// RAII flux_ctx; throws flux::Error with flux_last_error's text.
+class GpuContext {
+  public:
+    explicit GpuContext(int device);
+    ~GpuContext();
+    GpuContext(const GpuContext &) = delete;
+    GpuContext &operator=(const GpuContext &) = delete;
+    flux_ctx *get() const { return ctx_; }
+    int device() const { return device_; }
+    void check(int rc, const char *what) const;
+
+  private:
+    flux_ctx *ctx_ = nullptr;
+    int device_ = 0;
+};
+
+// Scene::from_data (scene.rs:128-154): plain data + job configuration, flattened for the device.
+struct Scene {
+    SceneData data;
+    JobConfiguration job_config;
+    std::unique_ptr<FlatScene> flat;
+    static Scene from_data(const SceneData &sd, const JobConfiguration &cfg);
+};
+
+// Camera::new + Camera::render (trace.rs:26-42, 53-97) on one GPU.  num_sets is the number of sample sets
+// (the reference passes image_width, workers.rs:50); the sets are generated on the device from `seed`
+// because the reference's come from an unseeded RNG.
+class Camera {
+  public:
+    static Camera create(GpuContext &ctx, const Scene &scene, const JobConfiguration &cfg, uint32_t num_sets, uint64_t seed);
+    WorkUnitResult render(const Scene &scene, const WorkUnit &unit) const;
+    std::vector<double> render_row_list(const std::vector<uint32_t> &rows) const;
+    float last_kernel_ms() const;
+
+  private:
+    Camera(GpuContext &ctx, uint32_t w, uint32_t h) : ctx_(&ctx), width_(w), height_(h) {}
+    GpuContext *ctx_;
+    uint32_t width_, height_;
+};
+
+// Third Worker beside LocalWorker / NetworkWorker (manager.rs:232-236).  One GpuWorker drives `devices`
+// GPUs of one box: interleaved tiles of `tile_rows` rows per GPU (flux_shard_rows) replace the shared
+// bounded(1) work queue (manager.rs:100); each GPU renders its shard on its own host thread and the rows
+// are assembled in host memory.
+class GpuWorker {
+  public:
+    GpuWorker(std::vector<int> devices, uint64_t seed, uint32_t tile_rows = 4);
+    WorkerInfo info() const;
+    // workers.rs:46-64 for one job: Scene::from_data, Camera::new, render every work unit -> image
+    Image render_job(const SceneData &sd, const JobConfiguration &cfg, double *render_seconds = nullptr);
+    // the single-GPU loop body itself, unit by unit (what a manager would drive)
+    std::vector<WorkUnitResult> run_job(const SceneData &sd, const JobConfiguration &cfg);
+
+  private:
+    std::vector<int> devices_;
+    uint64_t seed_;
+    uint32_t tile_rows_;
+};
+
+}  // namespace flux

@@ -1,0 +1,161 @@
+// fluxb200 — render driver mirroring the reference's `flux` binary (flux/src/main.rs:23-205) for the GPU path:
+//
+//   fluxb200 <scene_file> [-r ROOT] [-d DEPTH] [-R COUNT] [-G GPUS] [--seed S] [--width W --height H] [-o FILE]
+//
+// -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node, -L,
+// -g and -t have no counterpart: the network workers are replaced by the GPUs of this box (-G), there is no
+// local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
+// (manager.rs:330) unless -o is given.  --dump-flat FILE writes the flattened scene (no GPU needed; used by the
+// tests to compare this loader with the Python mirror).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "fluxhost.hpp"
+
+namespace {
+
+struct Config {   // flux/src/main.rs:114-124
+    std::string input_filename, output_filename, dump_flat;
+    uint32_t sample_root = 1, max_depth = 5, rows_per_work_unit = 50;
+    uint32_t gpus = 1, width = 0, height = 0;
+    uint64_t seed = 1;
+};
+
+[[noreturn]] void usage(const char *msg) {
+    if (msg) std::fprintf(stderr, "error: %s\n\n", msg);
+    std::fprintf(stderr,
+                 "fluxb200 — flux ray tracer, B200 render path\n\n"
+                 "USAGE:\n    fluxb200 [OPTIONS] <scene_file>\n\nOPTIONS:\n"
+                 "    -r, --root <ROOT>      Sample root (samples per pixel = ROOT^2) [default: 1]\n"
+                 "    -d, --depth <DEPTH>    Tracing depth [default: 5]\n"
+                 "    -R, --rows <COUNT>     Image rows per work unit [default: 50]\n"
+                 "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
+                 "        --seed <S>         Seed of the sample sets [default: 1]\n"
+                 "        --width <W> --height <H>   Override the scene's image size\n"
+                 "    -o <FILE>              Output file [default: <scene_name>.ppm]\n"
+                 "        --dump-flat <FILE> Write the flattened scene and exit (no GPU needed)\n");
+    std::exit(msg ? 2 : 0);
+}
+
+uint64_t parse_u64(const char *s, const char *what) {
+    char *end = nullptr;
+    if (!s || !*s || *s == '-') usage((std::string("invalid value for ") + what).c_str());
+    const unsigned long long v = std::strtoull(s, &end, 10);
+    if (*end) usage((std::string("invalid value for ") + what).c_str());   // usize::from_str(..).unwrap() panics
+    return v;
+}
+
+Config config_from_args(int argc, char **argv) {
+    Config c;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&](const char *what) -> const char * {
+            if (i + 1 >= argc) usage((std::string("missing value for ") + what).c_str());
+            return argv[++i];
+        };
+        if (a == "-r" || a == "--root") c.sample_root = (uint32_t)parse_u64(next("--root"), "--root");
+        else if (a == "-d" || a == "--depth") c.max_depth = (uint32_t)parse_u64(next("--depth"), "--depth");
+        else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
+        else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
+        else if (a == "--seed") c.seed = parse_u64(next("--seed"), "--seed");
+        else if (a == "--width") c.width = (uint32_t)parse_u64(next("--width"), "--width");
+        else if (a == "--height") c.height = (uint32_t)parse_u64(next("--height"), "--height");
+        else if (a == "-o") c.output_filename = next("-o");
+        else if (a == "--dump-flat") c.dump_flat = next("--dump-flat");
+        else if (a == "-h" || a == "--help") usage(nullptr);
+        else if (!a.empty() && a[0] == '-') usage(("unknown option " + a).c_str());
+        else if (c.input_filename.empty()) c.input_filename = a;
+        else usage("more than one scene file");
+    }
+    if (c.input_filename.empty()) usage("Scene filename is required");
+    if (c.sample_root == 0 || c.gpus == 0 || c.rows_per_work_unit == 0) usage("--root, --gpus and --rows must be >= 1");
+    return c;
+}
+
+// Flattened scene as text, doubles in hex-float so the comparison with the Python loader is exact.
+void dump_flat(const std::string &path, flux::FlatScene &f) {
+    FILE *o = std::fopen(path.c_str(), "w");
+    if (!o) throw flux::Error("cannot write `" + path + "`");
+    const flux_scene_flat &s = *f.ptr();
+    auto dv = [&](const char *name, const double *p, size_t n) {
+        std::fprintf(o, "%s %zu", name, n);
+        for (size_t i = 0; i < n; i++) std::fprintf(o, " %a", p[i]);
+        std::fprintf(o, "\n");
+    };
+    auto uv = [&](const char *name, const uint32_t *p, size_t n) {
+        std::fprintf(o, "%s %zu", name, n);
+        for (size_t i = 0; i < n; i++) std::fprintf(o, " %u", p[i]);
+        std::fprintf(o, "\n");
+    };
+    std::fprintf(o, "image %u %u\n", s.image_width, s.image_height);
+    const double scal[] = {s.pixel_size, s.zoom_factor, s.view_plane_distance, s.focal_distance, s.lens_radius};
+    dv("scalars", scal, 5);
+    dv("background", s.background, 3);
+    dv("eye", s.eye, 3);
+    dv("look_at", s.look_at, 3);
+    dv("up", s.up, 3);
+    std::fprintf(o, "materials %u\n", s.n_materials);
+    for (uint32_t i = 0; i < s.n_materials; i++) {
+        const flux_material &m = s.materials[i];
+        std::fprintf(o, "material %u %a %a %a %a %a\n", m.kind, m.color[0], m.color[1], m.color[2], m.k, m.exp);
+    }
+    dv("sphere_center", s.sphere_center, 3 * (size_t)s.n_spheres);
+    dv("sphere_radius", s.sphere_radius, s.n_spheres);
+    std::fprintf(o, "sphere_invert %u", s.n_spheres);
+    for (uint32_t i = 0; i < s.n_spheres; i++) std::fprintf(o, " %u", (unsigned)s.sphere_invert[i]);
+    std::fprintf(o, "\n");
+    uv("sphere_shape_id", s.sphere_shape_id, s.n_spheres);
+    uv("sphere_material", s.sphere_material, s.n_spheres);
+    dv("plane_point", s.plane_point, 3 * (size_t)s.n_planes);
+    dv("plane_normal", s.plane_normal, 3 * (size_t)s.n_planes);
+    uv("plane_shape_id", s.plane_shape_id, s.n_planes);
+    uv("plane_material", s.plane_material, s.n_planes);
+    dv("tri_v0", s.tri_v0, 3 * (size_t)s.n_triangles);
+    dv("tri_v1", s.tri_v1, 3 * (size_t)s.n_triangles);
+    dv("tri_v2", s.tri_v2, 3 * (size_t)s.n_triangles);
+    uv("tri_shape_id", s.tri_shape_id, s.n_triangles);
+    uv("tri_material", s.tri_material, s.n_triangles);
+    std::fclose(o);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    const Config config = config_from_args(argc, argv);
+    try {
+        // Load the YAML scene file (flux/src/main.rs:27-29)
+        flux::SceneData s = flux::SceneData::from_yaml_file(config.input_filename);
+        if (config.width && config.height) s = s.with_size(config.width, config.height);
+        if (!config.dump_flat.empty()) {
+            auto flat = s.flatten();
+            dump_flat(config.dump_flat, *flat);
+            return 0;
+        }
+        std::vector<int> devices;
+        for (uint32_t g = 0; g < config.gpus; g++) devices.push_back((int)g);
+        flux::GpuWorker worker(devices, config.seed);
+        std::printf("GPU worker ready, info:\n");
+        std::printf("Threads: %u\n", worker.info().num_threads);   // WorkerInfo::print, manager.rs:227-229
+        flux::JobConfiguration jobcfg;
+        jobcfg.sample_root = config.sample_root;
+        jobcfg.max_trace_depth = config.max_depth;
+        jobcfg.rows_per_work_unit = config.rows_per_work_unit;
+        std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),   // title(), main.rs:207-214
+                    jobcfg.sample_root * jobcfg.sample_root, jobcfg.sample_root == 1 ? "" : "s", jobcfg.max_trace_depth);
+        double seconds = 0.0;
+        flux::Image img = worker.render_job(s, jobcfg, &seconds);
+        std::printf("rendering finished, total time %.6fs\n", seconds);   // manager.rs:327
+        const double n = (double)img.width * img.height * jobcfg.sample_root * jobcfg.sample_root;
+        std::printf("%.1f Msamples/s on %u GPU(s)\n", n / seconds / 1e6, config.gpus);
+        const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
+        img.write(out);
+        std::printf("wrote %s\n", out.c_str());
+        std::printf("Shutting down\n");
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "fluxb200: %s\n", e.what());   // the reference unwrap()s: a panic with the error text
+        return 101;                                          // Rust's panic exit status
+    }
+    return 0;
+}
