@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--cpu-root", type=int, default=0, help="sample_root of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--kernel-mode", type=int, default=0, help="flux_set_kernel_mode (0 = auto); A/B timing only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -191,6 +192,7 @@ def main():
     cfg = JobConfiguration(root, MAX_DEPTH, 50)
     flat = sd.flatten()
     ctx = GpuContext(local_rank)
+    ctx.set_kernel_mode(args.kernel_mode)
     ctx.set_scene(flat, cfg)
     ctx.generate_samples(SEED, W)
     from flux_b200.sharding import FrameGather, FramePlan

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libfluxb200.so")
-SOURCES = ["api.cu", "bvh_build.cu", "render.cu", "render_regen.cu", "render_wave.cu", "samplegen.cu"]
+SOURCES = ["api.cu", "bvh_build.cu", "render.cu", "render_regen.cu", "render_wave.cu", "render_wave2.cu", "samplegen.cu"]
 
 # -fmad=false: the Rust reference never contracts a*b+c; bit parity of hit distances and
 # radiance depends on it.  Host code: -ffp-contract=off for the same reason.
@@ -35,18 +35,25 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra=(), out: str = LIB) -> str:
+    """Compile libfluxb200.so.  `extra` adds nvcc flags and `out` another output path: A/B variants of
+    compile-time kernel knobs (tools/build_variants.sh), selected at run time with FLUXB200_LIB."""
+    if out == LIB and not force and not needs_build():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-           "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+           "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    extra = [a for a in sys.argv[1:] if a != "-f"]
-    print(build(force=True, verbose=True, extra=extra))
+    args = [a for a in sys.argv[1:] if a != "-f"]
+    out = LIB
+    if "-o" in args:
+        k = args.index("-o")
+        out = os.path.abspath(args[k + 1])
+        del args[k:k + 2]
+    print(build(force=True, verbose=True, extra=args, out=out))

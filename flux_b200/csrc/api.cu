@@ -76,6 +76,8 @@ struct flux_ctx {
     DevBuf<TriRec> bvh_tri;
     DevBuf<uint32_t> bvh_prims, bvh_linear;
     uint32_t bvh_depth = 0, bvh_leaf = 0;
+    float cull[FLUX_CULL_MAX][4];   // f32 spheres for render_wave2.cu (RenderParams::cull)
+    float cull_cmax = 0.f;
 };
 
 namespace {
@@ -351,6 +353,27 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     sc.tri_meta = ctx->tri_meta.p;
     sc.materials = ctx->materials.p;
 
+    // ---- f32 spheres for the conservative slab pre-test (render_wave2.cu) ----
+    {
+        float cmax = 0.f;
+        const float up = std::numeric_limits<float>::infinity();
+        for (uint32_t i = 0; i < FLUX_CULL_MAX; i++) {
+            for (int k = 0; k < 4; k++) ctx->cull[i][k] = std::numeric_limits<float>::quiet_NaN();
+            if (i >= ns) continue;
+            const double c[3] = {sph[(size_t)SPH_CX * ns + i], sph[(size_t)SPH_CY * ns + i], sph[(size_t)SPH_CZ * ns + i]};
+            const double r = sph[(size_t)SPH_R * ns + i];
+            const bool ok = std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && std::isfinite(r) && r >= 0.0 &&
+                            std::fabs(c[0]) < 1e30 && std::fabs(c[1]) < 1e30 && std::fabs(c[2]) < 1e30 && r < 1e30;
+            if (!ok) continue;   // stays NaN: always the exact test
+            for (int k = 0; k < 3; k++) {
+                ctx->cull[i][k] = (float)c[k];
+                cmax = std::max(cmax, std::nextafter((float)(std::fabs(c[k]) + r), up));
+            }
+            ctx->cull[i][3] = (float)r;
+        }
+        ctx->cull_cmax = std::nextafter(cmax, up);
+    }
+
     // ---- acceleration structure (EXTENSION): the reference scans linearly (scene.rs:156-160); scenes beyond
     // FLUX_LINEAR_LIMIT bounded shapes get a BVH that returns the same answer (flux_bvh.cuh) ----
     ctx->bvh_depth = ctx->bvh_leaf = 0;
@@ -583,6 +606,8 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     p.out = d_out;
     p.counters = ctx->counters.p;
     p.work_counter = ctx->work_counter.p;
+    std::memcpy(p.cull, ctx->cull, sizeof(p.cull));
+    p.cull_cmax = ctx->cull_cmax;
     CK(cudaEventRecord(ctx->ev0, st));
     const bool regen_ok = regen_kernel_applicable(p);
     if (ctx->kernel_mode == 2 && !regen_ok)
@@ -590,7 +615,12 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     const bool wave_ok = wave_kernel_applicable(p);
     if (ctx->kernel_mode == 3 && !wave_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: wavefront kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
-    if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
+    const bool wave2_ok = wave2_kernel_applicable(p);
+    if (ctx->kernel_mode == 4 && !wave2_ok)
+        return fail(ctx, FLUX_ERR_INVALID, "render: wavefront-2 kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
+    if (wave2_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 4))
+        launch_render_wave2(p, ctx->count, ctx->sm_count, st);
+    else if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
         launch_render_wave(p, ctx->count, ctx->sm_count, st);
     else if (regen_ok && ctx->kernel_mode != 1)
         launch_render_regen(p, ctx->count, ctx->sm_count, st);
@@ -827,7 +857,7 @@ int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
 
 int flux_set_kernel_mode(flux_ctx *ctx, int mode) {
     if (!ctx) return FLUX_ERR_INVALID;
-    if (mode < 0 || mode > 3) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0..3");
+    if (mode < 0 || mode > 4) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0..4");
     ctx->kernel_mode = mode;
     return FLUX_OK;
 }

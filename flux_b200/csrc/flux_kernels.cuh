@@ -18,6 +18,12 @@ void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaSt
 bool wave_kernel_applicable(const RenderParams &p);
 void launch_render_wave(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
 
+// Second-generation block-local wavefront (render_wave2.cu): conservative FP32 slab pre-test from the constant
+// bank, terminated paths regenerated in the sorted item stage, 3 barriers per iteration.  Bit-identical to
+// render_wave.cu's output.
+bool wave2_kernel_applicable(const RenderParams &p);
+void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
+
 // Scene::hit on an explicit ray batch (scene.rs:156-160).
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
                        int sm_count, cudaStream_t stream);

@@ -71,6 +71,8 @@ struct DevSamples {
     uint32_t gk;
 };
 
+#define FLUX_CULL_MAX 64   // spheres covered by the constant-bank FP32 boxes (render_wave2.cu)
+
 struct RenderParams {
     DevScene scene;
     DevCamera cam;
@@ -81,6 +83,11 @@ struct RenderParams {
     double *out;                // [n_rows][W][3]
     unsigned long long *counters;  // flux_counters as u64[...] or null
     unsigned int *work_counter;    // dynamic work distribution
+    // spheres rounded to f32, {centre x, y, z, radius}, read as constant-bank operands by the conservative slab
+    // pre-test of render_wave2.cu; NaN for spheres that must always take the exact test (negative radius,
+    // non-finite) and for the unused entries.  cull_cmax >= max_k |centre_k| + radius over the valid spheres.
+    float cull[FLUX_CULL_MAX][4];
+    float cull_cmax;
 };
 
 // indices into flux_counters viewed as u64[]

@@ -1,0 +1,559 @@
+// render_wave2.cu — block-local wavefront render kernel, second generation.
+//
+// Same arithmetic as render.cu / render_regen.cu / render_wave.cu (Camera::render trace.rs:53-97 →
+// Scene::shade scene.rs:162-172 → Material::path_shade materials.rs:19-71); it re-divides the work after
+// what ncu showed on render_wave.cu (profiles/r1e_render_wave_full.txt: 169 warp instructions per sample,
+// 29 % of them FP64, issue slots 62 % busy, barrier stalls on top):
+//
+//   * the slab test BoundingBox::hit (shapes.rs:98-133) was 26 % of all issue slots at 42 instructions per
+//     test.  Here every sphere first gets a CONSERVATIVE FP32 slab test whose operands come from the
+//     kernel-parameter constant bank (uniform loads, FP32 pipe): 9 FFMA + 3 min/max + 2 compares classify the
+//     box as "certainly missed", "certainly hit" or "too close to call" with a rigorous error bound E; only
+//     the last class (rays grazing a box face within ~1e-4, degenerate rays) runs the exact FP64 test.  The
+//     pass/fail decisions — and therefore hit ids, distances and counters — are exactly the reference's;
+//   * ray generation ran with 18 of 32 lanes (only the slots that had just died).  Terminated paths are now
+//     one more "kind" of the sorted shading stage: one thread per ITEM unwinds the path's (f, w) stack,
+//     adds the radiance to the slot's running sum and generates the slot's next camera ray, at full warps;
+//   * the block-wide compaction of (slot, sphere) candidate pairs cost more issue slots (scan + publish +
+//     fold + 3 barriers) than it saved in the quadratic; the slot owner now walks its own candidate bits.
+//     One packed block scan and 3 barriers per iteration remain (was 3 scans and 8 barriers);
+//   * divisions that share a divisor share one reciprocal refinement (flux_math.cuh rcp_prepare/div_by,
+//     bit-identical to '/'): both roots by 2a, the sphere normal by r (refined once per CTA), normalize.
+//
+// A CTA owns one pixel and S = 256 path slots in shared memory.  Per iteration:
+//   1 owner     (thread = slot) FP32 cull + exact tests of the uncertain boxes, quadratics of the passing
+//               spheres in shape order (shapes.rs:176-212), planes (shapes.rs:137-139), closest hit
+//               (scene.rs:156-160, common.rs:17-23), hit record, classification
+//   2 bin       one packed prefix sum orders the slots by kind: matte | specular | glossy | terminated
+//   3 item      (thread = item) Matte / PerfectSpecular / GlossySpecular shading (materials.rs:19-71,
+//               brdf.rs:20-78) or unwind + accumulate + regenerate (materials.rs:31-32,69-70; trace.rs:72-82)
+//
+// Determinism: ranks come from prefix sums over slot order (no atomics); a slot's radiance sum is updated by
+// exactly one thread per iteration, in iteration order; slot sums are combined by a fixed tree.  A pixel's
+// value is therefore independent of grid size, scheduling and sharding, and equals
+// render_wave.cu's bit for bit (same slot/sample assignment, same summation order).
+#define FLUX_NORM_NOINLINE   // one copy of normalize3_dev per kernel: smaller hot instruction footprint (+1.4 % measured)
+#include "flux_kernels.cuh"
+#include "flux_shade.cuh"
+
+#ifndef WAVE2_S
+#define WAVE2_S 256          // path slots per CTA == threads per CTA
+#endif
+#ifndef WAVE2_MIN_BLOCKS
+#define WAVE2_MIN_BLOCKS (1024 / WAVE2_S)   // 64 registers per thread: 32 warps per SM
+#endif
+#define WAVE2_MAX_DEPTH 8    // deeper jobs use the other kernels
+
+namespace {
+
+// sphere record in shared memory (doubles)
+enum { V_C0X = 0, V_C1X, V_C0Y, V_C1Y, V_C0Z, V_C1Z, V_CX, V_CY, V_CZ, V_RR, V_RB, V_RY, V_INV, V_OK, V_SPH_STRIDE };
+enum { V_PPX = 0, V_PPY, V_PPZ, V_PNX, V_PNY, V_PNZ, V_PLN_STRIDE };
+// slot states
+enum { ST_IDLE = 0,    // no path and no sample left
+       ST_FRESH = 1,   // needs a camera ray, nothing to accumulate (start of a pixel)
+       ST_ALIVE = 2 }; // carries a ray
+// what the item stage does with a slot
+enum { K_NONE = 0, K_MATTE = 1, K_SPEC = 2, K_GLOSSY = 3, K_TERM = 4 };
+// how a path ended (payload of K_TERM)
+enum { T_FRESH = 0, T_BLACK = 1, T_BACKGROUND = 2, T_EMIT = 3 };
+
+// meta word: depth (0-7) | top (8-15) | material (16-27) | state (28-29) | term (30-31)
+__device__ __forceinline__ uint32_t meta_pack(uint32_t depth, uint32_t top, uint32_t mat, uint32_t st, uint32_t term) {
+    return depth | (top << 8) | (mat << 16) | (st << 28) | (term << 30);
+}
+__device__ __forceinline__ uint32_t meta_depth(uint32_t m) { return m & 0xFFu; }
+__device__ __forceinline__ uint32_t meta_top(uint32_t m) { return (m >> 8) & 0xFFu; }
+__device__ __forceinline__ uint32_t meta_mat(uint32_t m) { return (m >> 16) & 0xFFFu; }
+__device__ __forceinline__ uint32_t meta_state(uint32_t m) { return (m >> 28) & 3u; }
+__device__ __forceinline__ uint32_t meta_term(uint32_t m) { return (m >> 30) & 3u; }
+
+struct W2Smem {
+    double *sph, *pln;
+    DevMaterial *mat;
+    uint32_t *sph_id, *sph_mat, *pln_id, *pln_mat;
+    double *ox, *oy, *oz, *dx, *dy, *dz, *nx, *ny, *nz;
+    double *acc_r, *acc_g, *acc_b;
+    double *stk_w, *stk_lobe;   // [depth][slot]
+    uint8_t *stk_mat;           // [depth][slot]
+    uint32_t *si, *meta, *list;
+    unsigned long long *scr;    // [2][S/32] warp totals (double-buffered)
+};
+
+__host__ __device__ inline size_t w2_smem_bytes(uint32_t ns, uint32_t np, uint32_t nm, uint32_t max_depth) {
+    size_t b = 0;
+    b += (size_t)ns * V_SPH_STRIDE * 8 + (size_t)np * V_PLN_STRIDE * 8;
+    b += (size_t)nm * sizeof(DevMaterial);
+    b += (size_t)(2 * ns + 2 * np) * 4;
+    b = (b + 15) / 16 * 16;
+    b += (size_t)12 * WAVE2_S * 8;                     // ray, normal, radiance sums
+    b += (size_t)2 * max_depth * WAVE2_S * 8;          // stack weight, lobe
+    b += 2 * (WAVE2_S / 32) * 8;                       // scan scratch
+    b += (size_t)3 * WAVE2_S * 4;                      // si, meta, list
+    b += (size_t)max_depth * WAVE2_S;                  // stack material
+    return (b + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ W2Smem w2_carve(unsigned char *raw, uint32_t ns, uint32_t np, uint32_t nm, uint32_t max_depth) {
+    W2Smem w;
+    double *d = reinterpret_cast<double *>(raw);
+    w.sph = d; d += (size_t)ns * V_SPH_STRIDE;
+    w.pln = d; d += (size_t)np * V_PLN_STRIDE;
+    w.mat = reinterpret_cast<DevMaterial *>(d);
+    uint32_t *u = reinterpret_cast<uint32_t *>(w.mat + nm);
+    w.sph_id = u; u += ns;
+    w.sph_mat = u; u += ns;
+    w.pln_id = u; u += np;
+    w.pln_mat = u; u += np;
+    size_t off = (size_t)(reinterpret_cast<unsigned char *>(u) - raw);
+    off = (off + 15) / 16 * 16;
+    d = reinterpret_cast<double *>(raw + off);
+    w.ox = d; d += WAVE2_S; w.oy = d; d += WAVE2_S; w.oz = d; d += WAVE2_S;
+    w.dx = d; d += WAVE2_S; w.dy = d; d += WAVE2_S; w.dz = d; d += WAVE2_S;
+    w.nx = d; d += WAVE2_S; w.ny = d; d += WAVE2_S; w.nz = d; d += WAVE2_S;
+    w.acc_r = d; d += WAVE2_S; w.acc_g = d; d += WAVE2_S; w.acc_b = d; d += WAVE2_S;
+    w.stk_w = d; d += (size_t)max_depth * WAVE2_S;
+    w.stk_lobe = d; d += (size_t)max_depth * WAVE2_S;
+    w.scr = reinterpret_cast<unsigned long long *>(d); d += 2 * (WAVE2_S / 32);
+    u = reinterpret_cast<uint32_t *>(d);
+    w.si = u; u += WAVE2_S;
+    w.meta = u; u += WAVE2_S;
+    w.list = u; u += WAVE2_S;
+    w.stk_mat = reinterpret_cast<uint8_t *>(u);
+    return w;
+}
+
+// ---- conservative FP32 slab test against the constant-bank spheres ------------------------------------------
+// A sphere's box is centre -+ r on every axis (Sphere::new, shapes.rs:156-161), so with tc_k = (m_k - o_k) / d_k the
+// slab interval of axis k is tc_k -+ r |1/d_k|, whatever the sign of d_k.  In FP32, from f32-rounded m, r, 1/d and
+// o/d:   tc_k = fma(m_k, ia_k, -(o_k ia_k));  near_k = fma(-r, |ia_k|, tc_k);  far_k = fma(r, |ia_k|, tc_k)
+// each differs from the reference's double (c - o) * (1/d) by at most 2^-24 (4|m| + 3r + 3|o|) |ia|
+// <= E = 1.01 * 2^-21 * max_k |ia_k| (cmax + |o_k|)   (twice the bound), cmax >= |m_k| + r.  With
+//   s = min_k far_k - max(max_k near_k, T_MIN):
+//   s >  2E (+ rounding slack)  =>  t0 < t1 and t1 > T_MIN in the reference: the box is hit
+//   s < -2E (- rounding slack)  =>  t0 >= t1 or t1 < T_MIN in the reference: the box is missed
+// anything else — including every NaN / inf, for which no comparison holds — is "uncertain" and takes the exact
+// FP64 test.  Spheres with a negative or non-finite radius / centre carry NaN here and are always uncertain.
+struct CullRay {
+    float iax, iay, iaz, nox, noy, noz;   // 1/d and -(o * 1/d), rounded to f32
+    float aax, aay, aaz;                  // |1/d|
+    float e2;                             // 2E + slack
+};
+
+template <int BASE>
+__device__ __forceinline__ void cull16(const RenderParams &p, const CullRay &c, uint32_t ns, uint32_t &okm, uint32_t &failm) {
+#pragma unroll
+    for (int g = 0; g < 16; g += 4) {
+        if ((uint32_t)(BASE + g) < ns) {   // uniform; groups of 4 (entries past ns hold NaN and are masked off by the caller)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = BASE + g + j;
+                const float r = p.cull[i][3];
+                const float tcx = fmaf(p.cull[i][0], c.iax, c.nox);
+                const float tcy = fmaf(p.cull[i][1], c.iay, c.noy);
+                const float tcz = fmaf(p.cull[i][2], c.iaz, c.noz);
+                const float tn = fmaxf(fmaxf(fmaf(-r, c.aax, tcx), fmaf(-r, c.aay, tcy)), fmaxf(fmaf(-r, c.aaz, tcz), (float)FLUX_T_MIN));
+                const float tf = fminf(fminf(fmaf(r, c.aax, tcx), fmaf(r, c.aay, tcy)), fmaf(r, c.aaz, tcz));
+                const float sgap = tf - tn;
+                if (sgap > c.e2) okm |= 1u << (i & 31);
+                if (sgap < -c.e2) failm |= 1u << (i & 31);
+            }
+        }
+    }
+}
+
+// packed per-kind counters for the block scan: 16 bits each (matte | specular | glossy | terminated)
+__device__ __forceinline__ unsigned long long kind_one(uint32_t kind) {
+    return kind == K_NONE ? 0ull : (1ull << (16 * (kind - 1)));
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel(const __grid_constant__ RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t ns = p.scene.n_spheres, np = p.scene.n_planes, nm = p.scene.n_materials;
+    const uint32_t max_depth = p.cam.max_depth;
+    const W2Smem w = w2_carve(smem_raw, ns, np, nm, max_depth);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // ---- stage the scene (once per CTA) ----
+    for (uint32_t k = tid; k < ns; k += WAVE2_S) {
+        const double *g = p.scene.sph;
+        double *r = w.sph + (size_t)k * V_SPH_STRIDE;
+        r[V_C0X] = g[SPH_C0X * ns + k]; r[V_C1X] = g[SPH_C1X * ns + k];
+        r[V_C0Y] = g[SPH_C0Y * ns + k]; r[V_C1Y] = g[SPH_C1Y * ns + k];
+        r[V_C0Z] = g[SPH_C0Z * ns + k]; r[V_C1Z] = g[SPH_C1Z * ns + k];
+        r[V_CX] = g[SPH_CX * ns + k]; r[V_CY] = g[SPH_CY * ns + k]; r[V_CZ] = g[SPH_CZ * ns + k];
+        r[V_RR] = g[SPH_RR * ns + k];
+        const RcpD rr = rcp_prepare(g[SPH_R * ns + k]);   // the normal divides by r (shapes.rs:195): refine 1/r once
+        r[V_RB] = rr.b; r[V_RY] = rr.y; r[V_OK] = rr.ok ? 1.0 : 0.0;
+        r[V_INV] = g[SPH_INV * ns + k];
+        w.sph_id[k] = p.scene.sph_meta[k];
+        w.sph_mat[k] = p.scene.sph_meta[ns + k];
+    }
+    for (uint32_t k = tid; k < np; k += WAVE2_S) {
+        double *r = w.pln + (size_t)k * V_PLN_STRIDE;
+        for (int f = 0; f < PLN_FIELDS; f++) r[f] = p.scene.pln[(size_t)f * np + k];
+        w.pln_id[k] = p.scene.pln_meta[k];
+        w.pln_mat[k] = p.scene.pln_meta[np + k];
+    }
+    for (uint32_t k = tid; k < nm; k += WAVE2_S) w.mat[k] = p.scene.materials[k];
+    __syncthreads();
+
+    const DevCamera &cam = p.cam;
+    const uint32_t W = cam.W;
+    const uint32_t npix = p.n_rows * W;
+    const uint32_t n = p.ss.n;
+    unsigned long long cn[COUNT ? CN_COUNT : 1];
+    if (COUNT)
+        for (int k = 0; k < CN_COUNT; k++) cn[k] = 0;
+    const double pixel_denom = 1.0 / (double)((unsigned long long)p.ss.root * p.ss.root);  // trace.rs:59
+    const float cull_scale = 1.01f * 4.76837158203125e-07f;   // 1.01 * 2^-21
+    __shared__ uint32_t s_pixel;
+    __shared__ double s_red[3][WAVE2_S / 32];
+    uint32_t rot = 0;
+
+    for (;;) {
+        if (tid == 0) s_pixel = atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const uint32_t pixel = s_pixel;
+        if (pixel >= npix) break;
+        const uint32_t rk = pixel / W;
+        const uint32_t col = pixel - rk * W;
+        const uint32_t row = p.rows[rk];
+        const uint32_t set = p.set_index[(size_t)row * W + col];
+        const double2 *ps = p.ss.pixel + (size_t)set * n;
+        const double2 *ds = p.ss.disc + (size_t)set * n;
+        const double *hs = p.ss.hemi + (size_t)set * p.ss.max_depth * n * 3;
+        const double colf = (double)col - cam.half_w;           // trace.rs:72
+        const double rowf = (double)(cam.H - row) - cam.half_h; // trace.rs:73
+
+        uint32_t next = 0;   // next unassigned sample index (identical in all threads)
+        w.meta[tid] = meta_pack(0, 0, 0, ST_FRESH, T_FRESH);
+        w.acc_r[tid] = 0.0; w.acc_g[tid] = 0.0; w.acc_b[tid] = 0.0;
+        __syncthreads();
+
+        for (;;) {
+            // ======================= 1: owner — closest hit and classification =======================
+            uint32_t m = w.meta[tid];
+            uint32_t kind = K_NONE;
+            if (meta_state(m) == ST_FRESH) {
+                kind = K_TERM;   // payload T_FRESH: just generate the first ray
+            } else if (meta_state(m) == ST_ALIVE) {
+                const uint32_t depth = meta_depth(m), top = meta_top(m);
+                if (depth > max_depth) {   // scene.rs:164-165
+                    if (COUNT) cn[CN_DEPTH_CUT]++;
+                    kind = K_TERM;
+                    w.meta[tid] = meta_pack(depth, top, 0, ST_ALIVE, T_BLACK);
+                } else {
+                    if (COUNT) cn[CN_SEGMENTS]++;
+                    const V3 o = mk3(w.ox[tid], w.oy[tid], w.oz[tid]);
+                    const V3 d = mk3(w.dx[tid], w.dy[tid], w.dz[tid]);
+                    // ray-invariant terms (shapes.rs:107-122,177,180,187), hoisted
+                    const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
+                    // ---- conservative FP32 classification of every box ----
+                    unsigned long long mask, unc;
+                    {
+                        CullRay c;
+                        c.iax = (float)ia; c.iay = (float)ib; c.iaz = (float)ic;
+                        c.nox = -(float)(o.x * ia); c.noy = -(float)(o.y * ib); c.noz = -(float)(o.z * ic);
+                        c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
+                        const float ex = c.aax * (p.cull_cmax + fabsf((float)o.x));
+                        const float ey = c.aay * (p.cull_cmax + fabsf((float)o.y));
+                        const float ez = c.aaz * (p.cull_cmax + fabsf((float)o.z));
+                        const float E = fmaxf(fmaxf(ex, ey), ez) * cull_scale;
+                        // outside a sane range (NaN, inf, denormal reciprocals) nothing is decided in FP32
+                        c.e2 = (E > 1e-30f && E < 1e30f) ? 2.0f * E + 4e-9f : __int_as_float(0x7fc00000);
+                        uint32_t ok_lo = 0, ok_hi = 0, fail_lo = 0, fail_hi = 0;
+                        cull16<0>(p, c, ns, ok_lo, fail_lo);
+                        if (ns > 16) cull16<16>(p, c, ns, ok_lo, fail_lo);
+                        if (ns > 32) cull16<32>(p, c, ns, ok_hi, fail_hi);
+                        if (ns > 48) cull16<48>(p, c, ns, ok_hi, fail_hi);
+                        const unsigned long long valid = ns >= 64 ? ~0ull : ((1ull << ns) - 1ull);
+                        mask = (((unsigned long long)ok_hi << 32) | ok_lo) & valid;
+                        unc = ~((((unsigned long long)ok_hi << 32) | ok_lo) | (((unsigned long long)fail_hi << 32) | fail_lo)) & valid;
+                    }
+                    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
+                    while (unc) {   // exact BoundingBox::hit (shapes.rs:98-133) for the boxes FP32 could not decide
+                        const uint32_t j = (uint32_t)__ffsll((long long)unc) - 1u;
+                        unc &= unc - 1ull;
+                        const double *s = w.sph + (size_t)j * V_SPH_STRIDE;
+                        const double tx_min = (s[V_C0X + sx] - o.x) * ia, tx_max = (s[V_C1X - sx] - o.x) * ia;
+                        const double ty_min = (s[V_C0Y + sy] - o.y) * ib, ty_max = (s[V_C1Y - sy] - o.y) * ib;
+                        const double tz_min = (s[V_C0Z + sz] - o.z) * ic, tz_max = (s[V_C1Z - sz] - o.z) * ic;
+                        const double t0 = ref_max(tx_min, ref_max(ty_min, tz_min));
+                        const double t1 = ref_min(tx_max, ref_min(ty_max, tz_max));
+                        if (t0 < t1 && t1 > FLUX_T_MIN) mask |= 1ull << j;
+                    }
+                    if (COUNT) {
+                        cn[CN_BBOX_TESTS] += ns;
+                        cn[CN_BBOX_PASS] += __popcll(mask);
+                    }
+                    // ---- quadratics of the passing spheres, in shape order (shapes.rs:176-212) ----
+                    const double A = dot3(d, d);
+                    const double A4 = 4.0 * A;
+                    const RcpD rA2 = rcp_prepare(2.0 * A);
+                    double best_t = 0.0;
+                    uint32_t best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
+                    while (mask) {
+                        const uint32_t j = (uint32_t)__ffsll((long long)mask) - 1u;
+                        mask &= mask - 1ull;
+                        const double *s = w.sph + (size_t)j * V_SPH_STRIDE;
+                        const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
+                        const double b = 2.0 * dot3(temp, d);
+                        const double c = dot3(temp, temp) - s[V_RR];
+                        const double disc = b * b - A4 * c;
+                        if (disc < 0.0) continue;
+                        if (COUNT) cn[CN_DISC_NONNEG]++;
+                        const double e = sqrt(disc);
+                        double t = div_by(-b - e, rA2);
+                        if (!(t > FLUX_T_MIN)) {
+                            if (COUNT) cn[CN_T2]++;
+                            t = div_by(-b + e, rA2);
+                            if (!(t > FLUX_T_MIN)) continue;
+                        }
+                        if (COUNT) cn[CN_CANDIDATES]++;
+                        // a later sphere wins only if strictly closer (common.rs:17-23 + min_by)
+                        if (best_ref == 0xFFFFFFFFu || t < best_t) {
+                            best_t = t;
+                            best_ref = j;
+                        }
+                    }
+                    // ---- planes (shapes.rs:137-139) ----
+                    uint32_t best_id = best_ref == 0xFFFFFFFFu ? 0xFFFFFFFFu : w.sph_id[best_ref];
+                    const double *pl = w.pln;
+                    for (uint32_t i = 0; i < np; i++, pl += V_PLN_STRIDE) {
+                        if (COUNT) cn[CN_PLANE_TESTS]++;
+                        const V3 pn = mk3(pl[V_PNX], pl[V_PNY], pl[V_PNZ]);
+                        const double t = dot3(mk3(pl[V_PPX] - o.x, pl[V_PPY] - o.y, pl[V_PPZ] - o.z), pn) / dot3(d, pn);
+                        if (!(t > FLUX_T_MIN)) continue;
+                        if (COUNT) cn[CN_CANDIDATES]++;
+                        const uint32_t id = w.pln_id[i];
+                        if (best_id == 0xFFFFFFFFu || t < best_t || (t == best_t && id < best_id)) {
+                            best_t = t;
+                            best_id = id;
+                            best_ref = 0x80000000u | i;
+                        }
+                    }
+                    if (best_id == 0xFFFFFFFFu) {  // scene.rs:168
+                        if (COUNT) cn[CN_MISS]++;
+                        kind = K_TERM;
+                        w.meta[tid] = meta_pack(depth, top, 0, ST_ALIVE, T_BACKGROUND);
+                    } else {
+                        // hit record of the closest hit only (shapes.rs:140-147,191-198)
+                        V3 normal;
+                        uint32_t mi;
+                        if (best_ref & 0x80000000u) {
+                            const uint32_t k = best_ref & 0x7FFFFFFFu;
+                            const double *q = w.pln + (size_t)k * V_PLN_STRIDE;
+                            normal = mk3(q[V_PNX], q[V_PNY], q[V_PNZ]);
+                            mi = w.pln_mat[k];
+                            if (COUNT) cn[CN_HIT_PLANE]++;
+                        } else {
+                            const double *s = w.sph + (size_t)best_ref * V_SPH_STRIDE;
+                            const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
+                            const V3 nn = (temp + best_t * d) * s[V_INV];
+                            RcpD rr;
+                            rr.b = s[V_RB]; rr.y = s[V_RY]; rr.ok = s[V_OK] != 0.0;
+                            normal = V3{div_by(nn.x, rr), div_by(nn.y, rr), div_by(nn.z, rr)};
+                            mi = w.sph_mat[best_ref];
+                            if (COUNT) cn[CN_HIT_SPHERE]++;
+                        }
+                        const uint32_t mk = w.mat[mi].kind;
+                        if (mk == FLUX_MAT_EMISSIVE) {  // materials.rs:42-49
+                            if (COUNT) cn[CN_EMISSIVE]++;
+                            kind = K_TERM;
+                            w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, dot3(normal * -1.0, d) > 0.0 ? T_EMIT : T_BLACK);
+                        } else {
+                            kind = mk == FLUX_MAT_MATTE ? K_MATTE : (mk == FLUX_MAT_REFLECTIVE ? K_SPEC : K_GLOSSY);
+                            const V3 point = o + best_t * d;
+                            w.nx[tid] = normal.x; w.ny[tid] = normal.y; w.nz[tid] = normal.z;
+                            w.ox[tid] = point.x; w.oy[tid] = point.y; w.oz[tid] = point.z;  // child ray origin
+                            w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, 0);
+                        }
+                    }
+                }
+            }
+
+            // ======================= 2: bin the slots by kind (one packed scan) =======================
+            unsigned long long tot, ex;
+            {
+                const uint32_t bm = __ballot_sync(0xffffffffu, kind == K_MATTE);
+                const uint32_t bs = __ballot_sync(0xffffffffu, kind == K_SPEC);
+                const uint32_t bg = __ballot_sync(0xffffffffu, kind == K_GLOSSY);
+                const uint32_t bt = __ballot_sync(0xffffffffu, kind == K_TERM);
+                unsigned long long *scr = w.scr + (WAVE2_S / 32) * (rot++ & 1u);
+                if (lane == 0)
+                    scr[warp] = (unsigned long long)__popc(bm) | ((unsigned long long)__popc(bs) << 16) |
+                                ((unsigned long long)__popc(bg) << 32) | ((unsigned long long)__popc(bt) << 48);
+                const uint32_t mine = kind == K_MATTE ? bm : (kind == K_SPEC ? bs : (kind == K_GLOSSY ? bg : bt));
+                const uint32_t rank = __popc(mine & lt_mask);
+                __syncthreads();
+                unsigned long long base = 0;
+                tot = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < WAVE2_S / 32; q++) {
+                    const unsigned long long c = scr[q];
+                    if (q < warp) base += c;
+                    tot += c;
+                }
+                ex = base + (unsigned long long)rank * kind_one(kind);
+            }
+            const uint32_t n_matte = (uint32_t)(tot & 0xFFFFu), n_spec = (uint32_t)((tot >> 16) & 0xFFFFu);
+            const uint32_t n_gloss = (uint32_t)((tot >> 32) & 0xFFFFu), n_term = (uint32_t)((tot >> 48) & 0xFFFFu);
+            const uint32_t n_items = n_matte + n_spec + n_gloss + n_term;
+            if (n_items == 0) break;   // every slot idle (uniform)
+            if (kind == K_MATTE) w.list[(uint32_t)(ex & 0xFFFFu)] = tid;
+            else if (kind == K_SPEC) w.list[n_matte + (uint32_t)((ex >> 16) & 0xFFFFu)] = tid;
+            else if (kind == K_GLOSSY) w.list[n_matte + n_spec + (uint32_t)((ex >> 32) & 0xFFFFu)] = tid;
+            else if (kind == K_TERM) w.list[n_matte + n_spec + n_gloss + (uint32_t)((ex >> 48) & 0xFFFFu)] = tid;
+            __syncthreads();
+
+            // ======================= 3: one thread per item, in kind order =======================
+            if (tid < n_items) {
+                const uint32_t sl = w.list[tid];
+                const uint32_t sm = w.meta[sl];
+                const uint32_t depth = meta_depth(sm), top = meta_top(sm), mi = meta_mat(sm);
+                if (tid < n_matte + n_spec + n_gloss) {
+                    const V3 normal = mk3(w.nx[sl], w.ny[sl], w.nz[sl]);
+                    const V3 dir = mk3(w.dx[sl], w.dy[sl], w.dz[sl]);
+                    const uint32_t i = w.si[sl];
+                    V3 wi;
+                    double weight, lobe = 1.0;
+                    if (tid < n_matte) {  // materials.rs:19-33
+                        if (COUNT) cn[CN_MATTE]++;
+                        const double *hp = hs + ((size_t)(depth - 1) * n + i) * 3;
+                        matte_sample(normal, mk3(hp[0], hp[1], hp[2]), wi, weight);
+                    } else if (tid < n_matte + n_spec) {  // materials.rs:57-71, brdf.rs:39-45
+                        if (COUNT) cn[CN_SPECULAR]++;
+                        specular_sample(normal, dir, wi, weight);
+                    } else {  // materials.rs:57-71, brdf.rs:55-78
+                        if (COUNT) cn[CN_GLOSSY]++;
+                        const DevMaterial &gm = w.mat[mi];
+                        bool flipped;
+                        if (p.ss.ghemi) {  // lobe table: to_unit_hemi(pixel sample, exp) precomputed (same bits)
+                            const double *gh = p.ss.ghemi + (((size_t)set * p.ss.gk + gm.gidx) * n + i) * 3;
+                            glossy_sample_hs(normal, dir, mk3(gh[0], gh[1], gh[2]), gm.exp, wi, weight, lobe, flipped);
+                        } else {
+                            const double2 s = ps[i];
+                            glossy_sample(normal, dir, s.x, s.y, gm.exp, gm.inv_e1, wi, weight, lobe, flipped);
+                        }
+                        if (COUNT && flipped) cn[CN_GLOSSY_FLIP]++;
+                    }
+                    w.stk_w[(size_t)top * WAVE2_S + sl] = weight;
+                    w.stk_lobe[(size_t)top * WAVE2_S + sl] = lobe;
+                    w.stk_mat[(size_t)top * WAVE2_S + sl] = (uint8_t)mi;
+                    w.dx[sl] = wi.x; w.dy[sl] = wi.y; w.dz[sl] = wi.z;
+                    w.meta[sl] = meta_pack(depth + 1, top + 1, 0, ST_ALIVE, 0);
+                } else {
+                    // ---- a path ended: unwind, accumulate, start the slot's next path ----
+                    const uint32_t term = meta_term(sm);
+                    if (term != T_FRESH) {
+                        double Lr = 0.0, Lg = 0.0, Lb = 0.0;
+                        if (term == T_BACKGROUND) { Lr = cam.bg[0]; Lg = cam.bg[1]; Lb = cam.bg[2]; }
+                        else if (term == T_EMIT) { const DevMaterial &em = w.mat[mi]; Lr = em.c[0]; Lg = em.c[1]; Lb = em.c[2]; }
+                        uint32_t tp = top;
+                        while (tp > 0) {  // (f (*) L) * w, innermost first: materials.rs:31-32,69-70
+                            tp--;
+                            const DevMaterial &smat = w.mat[w.stk_mat[(size_t)tp * WAVE2_S + sl]];
+                            const double lobe = w.stk_lobe[(size_t)tp * WAVE2_S + sl];
+                            const double wt = w.stk_w[(size_t)tp * WAVE2_S + sl];
+                            Lr = ((smat.c[0] * lobe) * Lr) * wt;
+                            Lg = ((smat.c[1] * lobe) * Lg) * wt;
+                            Lb = ((smat.c[2] * lobe) * Lb) * wt;
+                        }
+                        w.acc_r[sl] += Lr;  // trace.rs:82 (this slot's paths, in completion order)
+                        w.acc_g[sl] += Lg;
+                        w.acc_b[sl] += Lb;
+                    }
+                    // terminated slots take the pixel's next sample indices in slot order
+                    const uint32_t i = next + (tid - (n_matte + n_spec + n_gloss));
+                    if (i < n) {
+                        const double2 s = ps[i];
+                        const double2 l = ds[i];
+                        // trace.rs:72-80 + Camera::ray_direction trace.rs:44-51
+                        const double u = cam.aps * (colf + s.x);
+                        const double v = cam.aps * (rowf + s.y);
+                        const double lpx = l.x * cam.lens_radius;
+                        const double lpy = l.y * cam.lens_radius;
+                        const double px2 = u * cam.factor;
+                        const double py2 = v * cam.factor;
+                        const V3 d = normalize3_dev(((px2 - lpx) * cam.u + (py2 - lpy) * cam.v) - cam.focal_w);
+                        const V3 o = (cam.eye + lpx * cam.u) + lpy * cam.v;
+                        w.ox[sl] = o.x; w.oy[sl] = o.y; w.oz[sl] = o.z;
+                        w.dx[sl] = d.x; w.dy[sl] = d.y; w.dz[sl] = d.z;
+                        w.si[sl] = i;
+                        w.meta[sl] = meta_pack(1, 0, 0, ST_ALIVE, 0);
+                        if (COUNT) cn[CN_SAMPLES]++;
+                    } else {
+                        w.meta[sl] = meta_pack(0, 0, 0, ST_IDLE, 0);
+                    }
+                }
+            }
+            next += n_term;
+            __syncthreads();
+        }
+
+        // ---- fixed-shape reduction of the 256 slot sums, then trace.rs:85-86 + color.rs:35-44 ----
+        double ar = w.acc_r[tid], ag = w.acc_g[tid], ab = w.acc_b[tid];
+#pragma unroll
+        for (uint32_t o2 = 16; o2 > 0; o2 >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o2);
+            ag += __shfl_xor_sync(0xffffffffu, ag, o2);
+            ab += __shfl_xor_sync(0xffffffffu, ab, o2);
+        }
+        if (lane == 0) {
+            s_red[0][warp] = ar;
+            s_red[1][warp] = ag;
+            s_red[2][warp] = ab;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tr[WAVE2_S / 32], tg[WAVE2_S / 32], tb[WAVE2_S / 32];
+            for (int k = 0; k < WAVE2_S / 32; k++) { tr[k] = s_red[0][k]; tg[k] = s_red[1][k]; tb[k] = s_red[2][k]; }
+            for (int st = 1; st < WAVE2_S / 32; st <<= 1)   // fixed pairwise tree over the 8 warp sums
+                for (int k = 0; k + st < WAVE2_S / 32; k += 2 * st) { tr[k] += tr[k + st]; tg[k] += tg[k + st]; tb[k] += tb[k + st]; }
+            double r = tr[0] * pixel_denom, g = tg[0] * pixel_denom, b = tb[0] * pixel_denom;
+            const double mx1 = r > g ? r : g;
+            const double mx2 = mx1 > b ? mx1 : b;
+            if (mx2 > 1.0) {
+                const double inv = 1.0 / mx2;
+                r *= inv;
+                g *= inv;
+                b *= inv;
+            }
+            double *out = p.out + (size_t)pixel * 3;
+            out[0] = r;
+            out[1] = g;
+            out[2] = b;
+        }
+        __syncthreads();
+    }
+    if (COUNT) {
+        for (int k = 0; k < CN_COUNT; k++)
+            if (cn[k]) atomicAdd(p.counters + k, cn[k]);
+    }
+}
+
+}  // namespace
+
+// Applies when a CTA can own a pixel (spp >= 4096 keeps the per-pixel drain tail under ~2 %), the scene has only
+// spheres and planes, at most 64 spheres / 255 materials, and depth <= 8.
+bool wave2_kernel_applicable(const RenderParams &p) {
+    return p.ss.n >= 4096 && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= FLUX_CULL_MAX &&
+           p.scene.n_materials <= 255 && p.cam.max_depth >= 1 && p.cam.max_depth <= WAVE2_MAX_DEPTH &&
+           w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth) <= (size_t)(226 * 1024) / WAVE2_MIN_BLOCKS - 1024;
+}
+
+void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
+    const size_t smem = w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth);
+    const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;
+    const uint64_t cap = (uint64_t)sm_count * WAVE2_MIN_BLOCKS;
+    const int blocks = (int)(npix < cap ? (npix ? npix : 1) : cap);
+    if (count) {
+        cudaFuncSetAttribute(render_wave2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_wave2_kernel<true><<<blocks, WAVE2_S, smem, stream>>>(p);
+    } else {
+        cudaFuncSetAttribute(render_wave2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_wave2_kernel<false><<<blocks, WAVE2_S, smem, stream>>>(p);
+    }
+}

@@ -344,7 +344,7 @@ def test_wavefront_kernel_matches_oracle_and_regen(gpu_ctx, demo2, scene_name):
     Hp.upload(gpu_ctx, flat, cfg, ss)
     imgs, cns = {}, {}
     try:
-        for mode in (2, 3):
+        for mode in (2, 3, 4):
             gpu_ctx.set_kernel_mode(mode)
             gpu_ctx.enable_counters(True)
             gpu_ctx.reset_counters()
@@ -360,7 +360,9 @@ def test_wavefront_kernel_matches_oracle_and_regen(gpu_ctx, demo2, scene_name):
     tol = 1e-12 if scene_name == "deterministic" else RADIANCE_RTOL
     assert Hp.rel_err(imgs[3], ref) <= tol
     assert Hp.rel_err(imgs[2], ref) <= tol
-    assert cns[2] == cns[3]
+    assert cns[2] == cns[3] == cns[4]
+    # second-generation wavefront: same slot/sample schedule and summation order as the first -> same bits
+    assert np.array_equal(imgs[4].view(np.uint64), imgs[3].view(np.uint64))
     for k, v in cn_o.items():
         assert abs(cns[3][k] - v) <= max(2, 1e-6 * v), (k, cns[3][k], v)
 
@@ -377,3 +379,37 @@ def test_wavefront_kernel_sharding_bitwise(gpu_ctx, demo2):
         rows = shard_rows(12, 2, rank, 4)
         parts[rows] = gpu_ctx.render_row_list(rows, 16)
     assert np.array_equal(full.view(np.uint64), parts.view(np.uint64))
+
+
+@pytest.mark.parametrize("eye_z,zoom", [(-9.0, 1.0), (-200.0, 22.0), (-1.0e4, 1100.0)])
+def test_wavefront2_conservative_fp32_box_test_is_exact(gpu_ctx, eye_z, zoom):
+    """render_wave2.cu decides most BoundingBox::hit tests (shapes.rs:98-133) in FP32 with an error bound and
+    falls back to the exact FP64 test when the bound cannot decide.  A distant camera makes the rays nearly
+    parallel to z (|1/d_x|, |1/d_y| up to 1e4): the bound widens until EVERY box is "uncertain", exercising the
+    fallback; the near camera exercises the FP32 decisions.  Pass counts must equal the oracle's exactly and the
+    image must match (deterministic materials: 1e-12)."""
+    from flux_b200.scene import CameraData, CameraSettings, SceneData
+    base = Hp.deterministic_scene(20, 14)
+    shapes = list(base.shapes[1:])   # without the environment sphere: the far cameras stand outside it
+    sd = SceneData("grazing", base.output_settings, (0.3, 0.4, 0.5), shapes,
+                   CameraSettings((0.3, 1.2, eye_z), (0.0, 1.0, 0.0), (0.0, 1.0, 0.0)),
+                   CameraData(zoom * 20 / 800.0, 500.0, abs(eye_z), 0.0))
+    cfg = JobConfiguration(64, 4, 50)
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(17, cfg, 20, 14)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    gpu_ctx.set_kernel_mode(4)
+    try:
+        gpu_ctx.enable_counters(True)
+        gpu_ctx.reset_counters()
+        img = gpu_ctx.render_rows(0, 13, 20)
+        cn = gpu_ctx.counters()
+    finally:
+        gpu_ctx.enable_counters(False)
+        gpu_ctx.set_kernel_mode(0)
+    ref, cn_o = O.render_rows(flat, cfg, ss, 0, 13, counters=True)
+    assert Hp.rel_err(img, ref) <= 1e-12
+    for k in ("samples", "segments", "bbox_tests", "bbox_pass", "disc_nonneg", "t2_evals", "candidates", "hit_sphere",
+              "hit_plane", "emissive", "matte", "specular", "depth_cut", "miss"):
+        assert cn[k] == cn_o[k], (k, cn[k], cn_o[k])
+    assert cn_o["hit_sphere"] > 0.2 * cn_o["samples"] and cn_o["miss"] > 0   # spheres in view, background behind

@@ -11,5 +11,5 @@ print("plain:", round(d["value"],1), "Msamples/s  frac", round(d["roofline"]["fr
 PY
 ncu --section SourceCounters --section InstructionStats --section WarpStateStats --section SchedulerStats \
     --section ComputeWorkloadAnalysis --section LaunchStats --section Occupancy --section SpeedOfLight \
-    --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -o gpurun_out/light_$TAG $CMD > gpurun_out/ncu_light_$TAG.log 2>&1
+    --clock-control none --import-source on -k regex:render_ -s ${SKIP:-3} -c 1 -o gpurun_out/light_$TAG $CMD > gpurun_out/ncu_light_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_light_$TAG.log
