@@ -44,6 +44,17 @@ __device__ __forceinline__ V3 to_unit_hemi_dev(double px, double py, double inv_
     return normalize3_dev(mk3(pu, pv, pw));
 }
 
+// x^y for the glossy lobe (brdf.rs:73, `powf`).  The reference's value comes from the platform libm and CUDA's pow
+// differs from it in the last ulp anyway (glossy radiance is pinned at 1e-6 relative, not bit-exact), so for the
+// ordinary case 0 < x < inf the lobe is exp(y * log(x)): |y ln x| stays below ~40 on the path (larger values
+// underflow the lobe), so the relative error is |y ln x| * 2^-52 < 1e-14 — eight orders inside the bar — for a
+// third of pow()'s instructions (pow was the critical path of the sorted shading stage).  Zero,
+// negative, infinite and NaN bases keep pow()'s special-case semantics.
+__device__ __forceinline__ double lobe_pow(double x, double y) {
+    if (x > 0.0 && x < 1.0e300) return exp(y * log(x));
+    return pow(x, y);
+}
+
 // Reflective + GlossySpecular: materials.rs:57-71 + brdf.rs:55-78, given hs = to_unit_hemi(pixel_sample, exp)
 // (brdf.rs:64).  lobe multiplies the per-material constant cs*ks to give f.
 __device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, double ex, V3 &wi, double &weight,
@@ -60,7 +71,7 @@ __device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, doubl
         wi = (u * -hs.x - v * hs.y) + w * hs.z;
     else
         wi = wi0;
-    lobe = pow(dot3(r, wi), ex);
+    lobe = lobe_pow(dot3(r, wi), ex);
     double pdf = lobe * dot3(normal, wi);
     weight = dot3(normal, wi) / pdf;
 }
