@@ -278,9 +278,21 @@ def main():
     ops_launch = algorithmic_ops(cn)
     peak_ginstr = ctx.measure_fp64_peak()
     achieved_tops = ops_launch / (last_kernel_ms * 1e-3) / 1e12
+    # DRAM traffic per launch: dram__bytes_read + dram__bytes_write of the render kernel from the committed
+    # `ncu --set full` capture (profiles/traffic.json says which), scaled by samples per launch
+    traffic, traffic_src, kernel_name = None, None, "render kernel (auto-selected)"
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        kernel_name = tj.get("kernel", kernel_name)
+        traffic = tj["dram_bytes_per_sample"] * cn["samples"]
+        traffic_src = tj.get("source")
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "fp64_pipe", "achieved": achieved_tops, "peak": peak_ginstr / 1e3, "unit": "TFLOP/s",
-                "frac": achieved_tops / (peak_ginstr / 1e3) if peak_ginstr else None, "traffic": None,
-                "kernel": "render_kernel", "kernel_ms": last_kernel_ms,
+                "frac": achieved_tops / (peak_ginstr / 1e3) if peak_ginstr else None, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes": cn["samples"] * 32 + cn["matte"] * 24 + cn["glossy"] * 24,
+                "kernel": kernel_name, "kernel_ms": last_kernel_ms,
                 "ops_per_sample": ops_launch / max(1, cn["samples"]),
                 "peak_source": "measured live: flux_measure_fp64_peak (unfused DADD/DMUL issue rate, FMA forbidden by parity)",
                 "hbm_algorithmic_GBps": (cn["samples"] * 32 + cn["matte"] * 24) / (last_kernel_ms * 1e-3) / 1e9}

@@ -71,7 +71,7 @@ struct DevSamples {
     uint32_t gk;
 };
 
-#define FLUX_CULL_MAX 64   // spheres covered by the constant-bank FP32 boxes (render_wave2.cu)
+#define FLUX_CULL_MAX 128  // spheres covered by the constant-bank FP32 table (render_wave2.cu)
 
 struct RenderParams {
     DevScene scene;

@@ -162,12 +162,82 @@ __device__ __forceinline__ void cull16(const RenderParams &p, const CullRay &c, 
     }
 }
 
+// (A/B'd and rejected, r1: prefetch.global.L1 of the hemisphere / lobe sample at classification time and of the next
+// window of camera samples — 6 % slower at both 4096 and 16384 spp; the loads' latency is already covered by the
+// other resident CTAs.)
+
 // packed per-kind counters for the block scan: 16 bits each (matte | specular | glossy | terminated)
 __device__ __forceinline__ unsigned long long kind_one(uint32_t kind) {
     return kind == K_NONE ? 0ull : (1ull << (16 * (kind - 1)));
 }
 
-template <bool COUNT>
+struct SphereScan {
+    double A4;      // 4.0 * a, shapes.rs:180
+    RcpD rA2;       // 2.0 * a, shapes.rs:187, with its refined reciprocal
+    double best_t;
+    uint32_t best_ref;
+};
+
+// Spheres [64 PASS, 64 PASS + 64): FP32 classification of every box, exact BoundingBox::hit (shapes.rs:98-133) for
+// the boxes FP32 could not decide, then the quadratics of the passing spheres in shape order (shapes.rs:176-212).
+template <int PASS, bool COUNT>
+__device__ __forceinline__ void sphere_pass(const RenderParams &p, const double *sph, const CullRay &c, uint32_t ns, V3 o, V3 d,
+                                            double ia, double ib, double ic, SphereScan &sc, unsigned long long *cn) {
+    constexpr int B = 64 * PASS;
+    const uint32_t nsb = ns - B < 64u ? ns - B : 64u;   // spheres in this pass (ns > B)
+    uint32_t ok_lo = 0, ok_hi = 0, fail_lo = 0, fail_hi = 0;
+    cull16<B>(p, c, ns, ok_lo, fail_lo);
+    if (ns > B + 16) cull16<B + 16>(p, c, ns, ok_lo, fail_lo);
+    if (ns > B + 32) cull16<B + 32>(p, c, ns, ok_hi, fail_hi);
+    if (ns > B + 48) cull16<B + 48>(p, c, ns, ok_hi, fail_hi);
+    const unsigned long long valid = nsb >= 64 ? ~0ull : ((1ull << nsb) - 1ull);
+    const unsigned long long okm = ((unsigned long long)ok_hi << 32) | ok_lo;
+    unsigned long long mask = okm & valid;
+    unsigned long long unc = ~(okm | (((unsigned long long)fail_hi << 32) | fail_lo)) & valid;
+    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
+    while (unc) {
+        const uint32_t j = (uint32_t)__ffsll((long long)unc) - 1u;
+        unc &= unc - 1ull;
+        const double *s = sph + (size_t)(B + j) * V_SPH_STRIDE;
+        const double tx_min = (s[V_C0X + sx] - o.x) * ia, tx_max = (s[V_C1X - sx] - o.x) * ia;
+        const double ty_min = (s[V_C0Y + sy] - o.y) * ib, ty_max = (s[V_C1Y - sy] - o.y) * ib;
+        const double tz_min = (s[V_C0Z + sz] - o.z) * ic, tz_max = (s[V_C1Z - sz] - o.z) * ic;
+        const double t0 = ref_max(tx_min, ref_max(ty_min, tz_min));
+        const double t1 = ref_min(tx_max, ref_min(ty_max, tz_max));
+        if (t0 < t1 && t1 > FLUX_T_MIN) mask |= 1ull << j;
+    }
+    if (COUNT) {
+        cn[CN_BBOX_TESTS] += nsb;
+        cn[CN_BBOX_PASS] += __popcll(mask);
+    }
+    while (mask) {
+        const uint32_t j = (uint32_t)__ffsll((long long)mask) - 1u;
+        mask &= mask - 1ull;
+        const double *s = sph + (size_t)(B + j) * V_SPH_STRIDE;
+        const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
+        const double b = 2.0 * dot3(temp, d);
+        const double cc = dot3(temp, temp) - s[V_RR];
+        const double disc = b * b - sc.A4 * cc;
+        if (disc < 0.0) continue;
+        if (COUNT) cn[CN_DISC_NONNEG]++;
+        const double e = sqrt(disc);
+        double t = div_by(-b - e, sc.rA2);
+        if (!(t > FLUX_T_MIN)) {
+            if (COUNT) cn[CN_T2]++;
+            t = div_by(-b + e, sc.rA2);
+            if (!(t > FLUX_T_MIN)) continue;
+        }
+        if (COUNT) cn[CN_CANDIDATES]++;
+        // spheres arrive in shape order: a later one wins only if strictly closer (common.rs:17-23 + min_by)
+        if (sc.best_ref == 0xFFFFFFFFu || t < sc.best_t) {
+            sc.best_t = t;
+            sc.best_ref = B + j;
+        }
+    }
+}
+
+// BIG: more than 64 spheres (second sphere pass); a separate instantiation so that the common case keeps its registers
+template <bool COUNT, bool BIG>
 __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t ns = p.scene.n_spheres, np = p.scene.n_planes, nm = p.scene.n_materials;
@@ -250,74 +320,29 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     const V3 d = mk3(w.dx[tid], w.dy[tid], w.dz[tid]);
                     // ray-invariant terms (shapes.rs:107-122,177,180,187), hoisted
                     const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
-                    // ---- conservative FP32 classification of every box ----
-                    unsigned long long mask, unc;
+                    // ---- spheres: conservative FP32 box classification, exact test where undecided, quadratics ----
+                    CullRay c;
+                    c.iax = (float)ia; c.iay = (float)ib; c.iaz = (float)ic;
+                    c.nox = -(float)(o.x * ia); c.noy = -(float)(o.y * ib); c.noz = -(float)(o.z * ic);
+                    c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
                     {
-                        CullRay c;
-                        c.iax = (float)ia; c.iay = (float)ib; c.iaz = (float)ic;
-                        c.nox = -(float)(o.x * ia); c.noy = -(float)(o.y * ib); c.noz = -(float)(o.z * ic);
-                        c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
                         const float ex = c.aax * (p.cull_cmax + fabsf((float)o.x));
                         const float ey = c.aay * (p.cull_cmax + fabsf((float)o.y));
                         const float ez = c.aaz * (p.cull_cmax + fabsf((float)o.z));
                         const float E = fmaxf(fmaxf(ex, ey), ez) * cull_scale;
                         // outside a sane range (NaN, inf, denormal reciprocals) nothing is decided in FP32
                         c.e2 = (E > 1e-30f && E < 1e30f) ? 2.0f * E + 4e-9f : __int_as_float(0x7fc00000);
-                        uint32_t ok_lo = 0, ok_hi = 0, fail_lo = 0, fail_hi = 0;
-                        cull16<0>(p, c, ns, ok_lo, fail_lo);
-                        if (ns > 16) cull16<16>(p, c, ns, ok_lo, fail_lo);
-                        if (ns > 32) cull16<32>(p, c, ns, ok_hi, fail_hi);
-                        if (ns > 48) cull16<48>(p, c, ns, ok_hi, fail_hi);
-                        const unsigned long long valid = ns >= 64 ? ~0ull : ((1ull << ns) - 1ull);
-                        mask = (((unsigned long long)ok_hi << 32) | ok_lo) & valid;
-                        unc = ~((((unsigned long long)ok_hi << 32) | ok_lo) | (((unsigned long long)fail_hi << 32) | fail_lo)) & valid;
                     }
-                    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
-                    while (unc) {   // exact BoundingBox::hit (shapes.rs:98-133) for the boxes FP32 could not decide
-                        const uint32_t j = (uint32_t)__ffsll((long long)unc) - 1u;
-                        unc &= unc - 1ull;
-                        const double *s = w.sph + (size_t)j * V_SPH_STRIDE;
-                        const double tx_min = (s[V_C0X + sx] - o.x) * ia, tx_max = (s[V_C1X - sx] - o.x) * ia;
-                        const double ty_min = (s[V_C0Y + sy] - o.y) * ib, ty_max = (s[V_C1Y - sy] - o.y) * ib;
-                        const double tz_min = (s[V_C0Z + sz] - o.z) * ic, tz_max = (s[V_C1Z - sz] - o.z) * ic;
-                        const double t0 = ref_max(tx_min, ref_max(ty_min, tz_min));
-                        const double t1 = ref_min(tx_max, ref_min(ty_max, tz_max));
-                        if (t0 < t1 && t1 > FLUX_T_MIN) mask |= 1ull << j;
-                    }
-                    if (COUNT) {
-                        cn[CN_BBOX_TESTS] += ns;
-                        cn[CN_BBOX_PASS] += __popcll(mask);
-                    }
-                    // ---- quadratics of the passing spheres, in shape order (shapes.rs:176-212) ----
                     const double A = dot3(d, d);
-                    const double A4 = 4.0 * A;
-                    const RcpD rA2 = rcp_prepare(2.0 * A);
-                    double best_t = 0.0;
-                    uint32_t best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
-                    while (mask) {
-                        const uint32_t j = (uint32_t)__ffsll((long long)mask) - 1u;
-                        mask &= mask - 1ull;
-                        const double *s = w.sph + (size_t)j * V_SPH_STRIDE;
-                        const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
-                        const double b = 2.0 * dot3(temp, d);
-                        const double c = dot3(temp, temp) - s[V_RR];
-                        const double disc = b * b - A4 * c;
-                        if (disc < 0.0) continue;
-                        if (COUNT) cn[CN_DISC_NONNEG]++;
-                        const double e = sqrt(disc);
-                        double t = div_by(-b - e, rA2);
-                        if (!(t > FLUX_T_MIN)) {
-                            if (COUNT) cn[CN_T2]++;
-                            t = div_by(-b + e, rA2);
-                            if (!(t > FLUX_T_MIN)) continue;
-                        }
-                        if (COUNT) cn[CN_CANDIDATES]++;
-                        // a later sphere wins only if strictly closer (common.rs:17-23 + min_by)
-                        if (best_ref == 0xFFFFFFFFu || t < best_t) {
-                            best_t = t;
-                            best_ref = j;
-                        }
-                    }
+                    SphereScan sc;
+                    sc.A4 = 4.0 * A;
+                    sc.rA2 = rcp_prepare(2.0 * A);
+                    sc.best_t = 0.0;
+                    sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
+                    sphere_pass<0, COUNT>(p, w.sph, c, ns, o, d, ia, ib, ic, sc, cn);
+                    if (BIG && ns > 64) sphere_pass<1, COUNT>(p, w.sph, c, ns, o, d, ia, ib, ic, sc, cn);
+                    double best_t = sc.best_t;
+                    uint32_t best_ref = sc.best_ref;
                     // ---- planes (shapes.rs:137-139) ----
                     uint32_t best_id = best_ref == 0xFFFFFFFFu ? 0xFFFFFFFFu : w.sph_id[best_ref];
                     const double *pl = w.pln;
@@ -537,11 +562,11 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 }  // namespace
 
 // Applies when a CTA can own a pixel (spp >= 4096 keeps the per-pixel drain tail under ~2 %), the scene has only
-// spheres and planes, at most 64 spheres / 255 materials, and depth <= 8.
+// spheres and planes, at most FLUX_CULL_MAX = 128 spheres / 255 materials, and depth <= 8.
 bool wave2_kernel_applicable(const RenderParams &p) {
     return p.ss.n >= 4096 && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= FLUX_CULL_MAX &&
            p.scene.n_materials <= 255 && p.cam.max_depth >= 1 && p.cam.max_depth <= WAVE2_MAX_DEPTH &&
-           w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth) <= (size_t)(226 * 1024) / WAVE2_MIN_BLOCKS - 1024;
+           w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth) <= (size_t)(226 * 1024) / 3 - 1024;   // at least 3 CTAs per SM
 }
 
 void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
@@ -549,11 +574,16 @@ void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaSt
     const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;
     const uint64_t cap = (uint64_t)sm_count * WAVE2_MIN_BLOCKS;
     const int blocks = (int)(npix < cap ? (npix ? npix : 1) : cap);
+    const bool big = p.scene.n_spheres > 64;
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, WAVE2_S, smem, stream>>>(p);
+    };
     if (count) {
-        cudaFuncSetAttribute(render_wave2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_wave2_kernel<true><<<blocks, WAVE2_S, smem, stream>>>(p);
+        if (big) go(render_wave2_kernel<true, true>);
+        else go(render_wave2_kernel<true, false>);
     } else {
-        cudaFuncSetAttribute(render_wave2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_wave2_kernel<false><<<blocks, WAVE2_S, smem, stream>>>(p);
+        if (big) go(render_wave2_kernel<false, true>);
+        else go(render_wave2_kernel<false, false>);
     }
 }

@@ -413,3 +413,31 @@ def test_wavefront2_conservative_fp32_box_test_is_exact(gpu_ctx, eye_z, zoom):
               "hit_plane", "emissive", "matte", "specular", "depth_cut", "miss"):
         assert cn[k] == cn_o[k], (k, cn[k], cn_o[k])
     assert cn_o["hit_sphere"] > 0.2 * cn_o["samples"] and cn_o["miss"] > 0   # spheres in view, background behind
+
+
+def test_wavefront2_divergent_glossy_scene_with_67_spheres(gpu_ctx):
+    """BASELINE config 4 shape (area lights + matte / glossy x3 / perfect-specular spheres, 67 spheres + floor) at a size
+    the oracle finishes: the second sphere pass (> 64 spheres) and all four shading kinds of the sorted item stage."""
+    from flux_b200 import synth
+    sd = synth.glossy_scene(24, 14, seed=4)
+    cfg = JobConfiguration(64, 5, 50)
+    flat = sd.flatten()
+    assert flat.struct.n_spheres == 67
+    ss = Hp.oracle_samples(23, cfg, 24, 14)
+    gpu_ctx.set_accel_mode(1)   # auto mode gives scenes beyond 40 bounded shapes to the BVH kernel
+    gpu_ctx.set_kernel_mode(4)
+    try:
+        Hp.upload(gpu_ctx, flat, cfg, ss)
+        gpu_ctx.enable_counters(True)
+        gpu_ctx.reset_counters()
+        img = gpu_ctx.render_rows(0, 13, 24)
+        cn = gpu_ctx.counters()
+    finally:
+        gpu_ctx.enable_counters(False)
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.set_accel_mode(0)
+    ref, cn_o = O.render_rows(flat, cfg, ss, 0, 13, counters=True)
+    assert Hp.rel_err(img, ref) <= RADIANCE_RTOL
+    for k, v in cn_o.items():
+        assert abs(cn[k] - v) <= max(2, 1e-6 * v), (k, cn[k], v)
+    assert min(cn_o["matte"], cn_o["glossy"], cn_o["specular"], cn_o["emissive"]) > 0
