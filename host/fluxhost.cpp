@@ -658,6 +658,8 @@ GpuWorker::GpuWorker(std::vector<int> devices, uint64_t seed, uint32_t tile_rows
     : devices_(std::move(devices)), seed_(seed), tile_rows_(tile_rows) {
     if (devices_.empty()) throw Error("GpuWorker: no devices");
     if (tile_rows_ == 0) throw Error("GpuWorker: tile_rows must be >= 1");
+    // device contexts belong to the worker, not to a job (workers.rs:26-41 builds the thread pool once)
+    for (int d : devices_) contexts_.push_back(std::make_unique<GpuContext>(d));
 }
 
 WorkerInfo GpuWorker::info() const {
@@ -668,7 +670,7 @@ WorkerInfo GpuWorker::info() const {
 
 std::vector<WorkUnitResult> GpuWorker::run_job(const SceneData &sd, const JobConfiguration &cfg) {
     Scene scene = Scene::from_data(sd, cfg);
-    GpuContext ctx(devices_[0]);
+    GpuContext &ctx = *contexts_[0];
     Camera camera = Camera::create(ctx, scene, cfg, sd.output_settings.image_width, seed_);
     std::vector<WorkUnitResult> out;
     for (const WorkUnit &u : work_units(sd.output_settings.image_height, cfg.rows_per_work_unit)) out.push_back(camera.render(scene, u));
@@ -690,7 +692,7 @@ Image GpuWorker::render_job(const SceneData &sd, const JobConfiguration &cfg, do
             std::vector<uint32_t> rows(n);
             flux_shard_rows(H, tile_rows_, rank, world, rows.data(), &n);
             if (n == 0) return;
-            GpuContext ctx(devices_[rank]);
+            GpuContext &ctx = *contexts_[rank];
             Camera camera = Camera::create(ctx, scene, cfg, W, seed_);   // same seed on every GPU: identical sample sets
             const std::vector<double> px = camera.render_row_list(rows);
             const size_t row_elems = (size_t)W * 3;

@@ -162,6 +162,7 @@ class GpuWorker {
 
   private:
     std::vector<int> devices_;
+    std::vector<std::unique_ptr<GpuContext>> contexts_;   // created with the worker, like LocalWorker::new builds its pool
     uint64_t seed_;
     uint32_t tile_rows_;
 };
