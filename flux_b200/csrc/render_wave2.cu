@@ -127,8 +127,10 @@ __device__ __forceinline__ W2Smem w2_carve(unsigned char *raw, uint32_t ns, uint
 // A sphere's box is centre -+ r on every axis (Sphere::new, shapes.rs:156-161), so with tc_k = (m_k - o_k) / d_k the
 // slab interval of axis k is tc_k -+ r |1/d_k|, whatever the sign of d_k.  In FP32, from f32-rounded m, r, 1/d and
 // o/d:   tc_k = fma(m_k, ia_k, -(o_k ia_k));  near_k = fma(-r, |ia_k|, tc_k);  far_k = fma(r, |ia_k|, tc_k)
-// each differs from the reference's double (c - o) * (1/d) by at most 2^-24 (4|m| + 3r + 3|o|) |ia|
-// <= E = 1.01 * 2^-21 * max_k |ia_k| (cmax + |o_k|)   (twice the bound), cmax >= |m_k| + r.  With
+// with ia_k = rcp((float)d_k) (relative error <= 2^-22 including the rounding of d_k) and o_k ia_k one more f32
+// product, each slab value differs from the reference's double (c - o) * (1/d) by at most
+// (2^-22 + 2^-23)(|m| + |o| + r)|ia| + 2^-24 (|tc| + |near|)  <=  1.4 * 2^-21 (cmax + |o_k|) |ia_k|
+// <= E = 1.01 * 2^-20 * max_k |ia_k| (cmax + |o_k|), cmax >= |m_k| + r.  With
 //   s = min_k far_k - max(max_k near_k, T_MIN):
 //   s >  2E (+ rounding slack)  =>  t0 < t1 and t1 > T_MIN in the reference: the box is hit
 //   s < -2E (- rounding slack)  =>  t0 >= t1 or t1 < T_MIN in the reference: the box is missed
@@ -139,6 +141,13 @@ struct CullRay {
     float aax, aay, aaz;                  // |1/d|
     float e2;                             // 2E + slack
 };
+
+// MUFU.RCP: maximum relative error 2^-23 (PTX ISA, rcp.approx.f32); 1/0 = inf, denormal inputs behave as written
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int BASE>
 __device__ __forceinline__ void cull16(const RenderParams &p, const CullRay &c, uint32_t ns, uint32_t &okm, uint32_t &failm) {
@@ -182,7 +191,7 @@ struct SphereScan {
 // the boxes FP32 could not decide, then the quadratics of the passing spheres in shape order (shapes.rs:176-212).
 template <int PASS, bool COUNT>
 __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double *sph, const CullRay &c, uint32_t ns, V3 o, V3 d,
-                                            double ia, double ib, double ic, SphereScan &sc, unsigned long long *cn) {
+                                            SphereScan &sc, unsigned long long *cn) {
     constexpr int B = 64 * PASS;
     const uint32_t nsb = ns - B < 64u ? ns - B : 64u;   // spheres in this pass (ns > B)
     uint32_t ok_lo = 0, ok_hi = 0, fail_lo = 0, fail_hi = 0;
@@ -194,8 +203,10 @@ __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double 
     const unsigned long long okm = ((unsigned long long)ok_hi << 32) | ok_lo;
     unsigned long long mask = okm & valid;
     unsigned long long unc = ~(okm | (((unsigned long long)fail_hi << 32) | fail_lo)) & valid;
-    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
     while (unc) {
+        // the exact reciprocals (shapes.rs:107,114,121) are needed on this rare path only
+        const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
+        const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
         const uint32_t j = (uint32_t)__ffsll((long long)unc) - 1u;
         unc &= unc - 1ull;
         const double *s = sph + (size_t)(B + j) * V_SPH_STRIDE;
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
     if (COUNT)
         for (int k = 0; k < CN_COUNT; k++) cn[k] = 0;
     const double pixel_denom = 1.0 / (double)((unsigned long long)p.ss.root * p.ss.root);  // trace.rs:59
-    const float cull_scale = 1.01f * 4.76837158203125e-07f;   // 1.01 * 2^-21
+    const float cull_scale = 1.01f * 9.5367431640625e-07f;   // 1.01 * 2^-20
     __shared__ uint32_t s_pixel;
     __shared__ double s_red[3][WAVE2_S / 32];
     uint32_t rot = 0;
@@ -318,17 +329,18 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     if (COUNT) cn[CN_SEGMENTS]++;
                     const V3 o = mk3(w.ox[tid], w.oy[tid], w.oz[tid]);
                     const V3 d = mk3(w.dx[tid], w.dy[tid], w.dz[tid]);
-                    // ray-invariant terms (shapes.rs:107-122,177,180,187), hoisted
-                    const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
                     // ---- spheres: conservative FP32 box classification, exact test where undecided, quadratics ----
+                    // 1/d in f32 from MUFU.RCP (the approximation error is part of E); the exact f64 reciprocals of
+                    // BoundingBox::hit are formed only where a box needs the exact test
                     CullRay c;
-                    c.iax = (float)ia; c.iay = (float)ib; c.iaz = (float)ic;
-                    c.nox = -(float)(o.x * ia); c.noy = -(float)(o.y * ib); c.noz = -(float)(o.z * ic);
+                    c.iax = rcp_approx((float)d.x); c.iay = rcp_approx((float)d.y); c.iaz = rcp_approx((float)d.z);
+                    const float ofx = (float)o.x, ofy = (float)o.y, ofz = (float)o.z;
+                    c.nox = -(ofx * c.iax); c.noy = -(ofy * c.iay); c.noz = -(ofz * c.iaz);
                     c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
                     {
-                        const float ex = c.aax * (p.cull_cmax + fabsf((float)o.x));
-                        const float ey = c.aay * (p.cull_cmax + fabsf((float)o.y));
-                        const float ez = c.aaz * (p.cull_cmax + fabsf((float)o.z));
+                        const float ex = c.aax * (p.cull_cmax + fabsf(ofx));
+                        const float ey = c.aay * (p.cull_cmax + fabsf(ofy));
+                        const float ez = c.aaz * (p.cull_cmax + fabsf(ofz));
                         const float E = fmaxf(fmaxf(ex, ey), ez) * cull_scale;
                         // outside a sane range (NaN, inf, denormal reciprocals) nothing is decided in FP32
                         c.e2 = (E > 1e-30f && E < 1e30f) ? 2.0f * E + 4e-9f : __int_as_float(0x7fc00000);
@@ -339,8 +351,8 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     sc.rA2 = rcp_prepare(2.0 * A);
                     sc.best_t = 0.0;
                     sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
-                    sphere_pass<0, COUNT>(p, w.sph, c, ns, o, d, ia, ib, ic, sc, cn);
-                    if (BIG && ns > 64) sphere_pass<1, COUNT>(p, w.sph, c, ns, o, d, ia, ib, ic, sc, cn);
+                    sphere_pass<0, COUNT>(p, w.sph, c, ns, o, d, sc, cn);
+                    if (BIG && ns > 64) sphere_pass<1, COUNT>(p, w.sph, c, ns, o, d, sc, cn);
                     double best_t = sc.best_t;
                     uint32_t best_ref = sc.best_ref;
                     // ---- planes (shapes.rs:137-139) ----
