@@ -297,6 +297,18 @@ def main():
                 "peak_source": "measured live: flux_measure_fp64_peak (unfused DADD/DMUL issue rate, FMA forbidden by parity)",
                 "hbm_algorithmic_GBps": (cn["samples"] * 32 + cn["matte"] * 24) / (last_kernel_ms * 1e-3) / 1e9}
 
+    # the memory side, against the driver-measured HBM figure (not the binding roofline: DESIGN.md §4)
+    hbm_peak, hbm_src = 7700.0, "fallback: B200_PROFILING.md nominal HBM3e"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+    except (OSError, KeyError, ValueError):
+        pass
+    alg_gbs = roofline["algorithmic_bytes"] / (last_kernel_ms * 1e-3) / 1e9
+    roofline_hbm = {"bound": "hbm", "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak,
+                    "traffic": traffic, "peak_source": hbm_src,
+                    "note": "not the bound: the path is FP64-issue bound (no dense contraction, 919 FP64 ops per 66-byte sample)"}
+
     line = None
     if rank == 0:
         cpu = None
@@ -313,7 +325,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": value / 5.314, "dtype": "f64", "data": "synthetic",
             "config": workload_config(root, world), "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "render_time_s_16384spp": W * H * 16384 / (value * 1e6),
             "vs_baseline_note": "value / 5.314 Msamples/s = README.md:1 (1479.9 s, 44 cores, unknown CPU)",
         }
