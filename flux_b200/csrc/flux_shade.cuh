@@ -20,7 +20,7 @@ __device__ __forceinline__ void matte_sample(V3 normal, V3 hemi, V3 &wi, double 
     wi = normalize3_dev((hemi.x * u + hemi.y * v) + hemi.z * w);
     double pdf = dot3(normal, wi) * FLUX_INV_PI;
     double ndotwi = dot3(normal, wi);
-    weight = ndotwi / pdf;
+    weight = div_full(ndotwi, pdf);
 }
 
 // Reflective + PerfectSpecular: materials.rs:57-71 + brdf.rs:39-45.
@@ -29,7 +29,7 @@ __device__ __forceinline__ void specular_sample(V3 normal, V3 dir, V3 &wi, doubl
     double ndotwo = dot3(normal, wo);
     wi = neg3(wo) + normal * ndotwo * 2.0;
     double pdf = dot3(normal, wi);
-    weight = dot3(normal, wi) / pdf;
+    weight = div_full(dot3(normal, wi), pdf);
 }
 
 // samplers/src/lib.rs:133-142 with inv_e1 = 1.0/(e+1.0) precomputed.
@@ -73,7 +73,7 @@ __device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, doubl
         wi = wi0;
     lobe = lobe_pow(dot3(r, wi), ex);
     double pdf = lobe * dot3(normal, wi);
-    weight = dot3(normal, wi) / pdf;
+    weight = div_full(dot3(normal, wi), pdf);
 }
 
 __device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, double sqy, double ex, double inv_e1,

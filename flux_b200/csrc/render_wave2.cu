@@ -149,25 +149,33 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-template <int BASE>
-__device__ __forceinline__ void cull16(const RenderParams &p, const CullRay &c, uint32_t ns, uint32_t &okm, uint32_t &failm) {
+// Box classification of spheres [base, base + count): groups of 4 in a run-time loop, constant-bank operands through
+// a uniform index.  (Fully unrolled with immediate constant offsets it was 8.6 % slower, r1: 150 more instructions
+// in a hot loop that already fills the 32 KB L1.5 instruction cache; groups of 1 / 2 / 8: -1.3 % / 0 / -5 %.)
+// Entries past the last sphere hold NaN (undecided) and are masked off by the caller.
+#ifndef WAVE2_CULL_GROUP
+#define WAVE2_CULL_GROUP 4
+#endif
+__device__ __forceinline__ void cull_boxes(const RenderParams &p, const CullRay &c, uint32_t base, uint32_t count,
+                                           unsigned long long &okm, unsigned long long &failm) {
+#pragma unroll 1
+    for (uint32_t g = 0; g < count; g += WAVE2_CULL_GROUP) {
+        uint32_t ok = 0, fail = 0;
 #pragma unroll
-    for (int g = 0; g < 16; g += 4) {
-        if ((uint32_t)(BASE + g) < ns) {   // uniform; groups of 4 (entries past ns hold NaN and are masked off by the caller)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int i = BASE + g + j;
-                const float r = p.cull[i][3];
-                const float tcx = fmaf(p.cull[i][0], c.iax, c.nox);
-                const float tcy = fmaf(p.cull[i][1], c.iay, c.noy);
-                const float tcz = fmaf(p.cull[i][2], c.iaz, c.noz);
-                const float tn = fmaxf(fmaxf(fmaf(-r, c.aax, tcx), fmaf(-r, c.aay, tcy)), fmaxf(fmaf(-r, c.aaz, tcz), (float)FLUX_T_MIN));
-                const float tf = fminf(fminf(fmaf(r, c.aax, tcx), fmaf(r, c.aay, tcy)), fmaf(r, c.aaz, tcz));
-                const float sgap = tf - tn;
-                if (sgap > c.e2) okm |= 1u << (i & 31);
-                if (sgap < -c.e2) failm |= 1u << (i & 31);
-            }
+        for (uint32_t j = 0; j < WAVE2_CULL_GROUP; j++) {
+            const uint32_t i = base + g + j;
+            const float r = p.cull[i][3];
+            const float tcx = fmaf(p.cull[i][0], c.iax, c.nox);
+            const float tcy = fmaf(p.cull[i][1], c.iay, c.noy);
+            const float tcz = fmaf(p.cull[i][2], c.iaz, c.noz);
+            const float tn = fmaxf(fmaxf(fmaf(-r, c.aax, tcx), fmaf(-r, c.aay, tcy)), fmaxf(fmaf(-r, c.aaz, tcz), (float)FLUX_T_MIN));
+            const float tf = fminf(fminf(fmaf(r, c.aax, tcx), fmaf(r, c.aay, tcy)), fmaf(r, c.aaz, tcz));
+            const float sgap = tf - tn;
+            if (sgap > c.e2) ok |= 1u << j;
+            if (sgap < -c.e2) fail |= 1u << j;
         }
+        okm |= (unsigned long long)ok << g;
+        failm |= (unsigned long long)fail << g;
     }
 }
 
@@ -194,15 +202,11 @@ __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double 
                                             SphereScan &sc, unsigned long long *cn) {
     constexpr int B = 64 * PASS;
     const uint32_t nsb = ns - B < 64u ? ns - B : 64u;   // spheres in this pass (ns > B)
-    uint32_t ok_lo = 0, ok_hi = 0, fail_lo = 0, fail_hi = 0;
-    cull16<B>(p, c, ns, ok_lo, fail_lo);
-    if (ns > B + 16) cull16<B + 16>(p, c, ns, ok_lo, fail_lo);
-    if (ns > B + 32) cull16<B + 32>(p, c, ns, ok_hi, fail_hi);
-    if (ns > B + 48) cull16<B + 48>(p, c, ns, ok_hi, fail_hi);
+    unsigned long long okm = 0ull, failm = 0ull;
+    cull_boxes(p, c, B, nsb, okm, failm);
     const unsigned long long valid = nsb >= 64 ? ~0ull : ((1ull << nsb) - 1ull);
-    const unsigned long long okm = ((unsigned long long)ok_hi << 32) | ok_lo;
     unsigned long long mask = okm & valid;
-    unsigned long long unc = ~(okm | (((unsigned long long)fail_hi << 32) | fail_lo)) & valid;
+    unsigned long long unc = ~(okm | failm) & valid;
     while (unc) {
         // the exact reciprocals (shapes.rs:107,114,121) are needed on this rare path only
         const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     for (uint32_t i = 0; i < np; i++, pl += V_PLN_STRIDE) {
                         if (COUNT) cn[CN_PLANE_TESTS]++;
                         const V3 pn = mk3(pl[V_PNX], pl[V_PNY], pl[V_PNZ]);
-                        const double t = dot3(mk3(pl[V_PPX] - o.x, pl[V_PPY] - o.y, pl[V_PPZ] - o.z), pn) / dot3(d, pn);
+                        const double t = div_full(dot3(mk3(pl[V_PPX] - o.x, pl[V_PPY] - o.y, pl[V_PPZ] - o.z), pn), dot3(d, pn));
                         if (!(t > FLUX_T_MIN)) continue;
                         if (COUNT) cn[CN_CANDIDATES]++;
                         const uint32_t id = w.pln_id[i];
