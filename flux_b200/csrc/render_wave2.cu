@@ -157,7 +157,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 #define WAVE2_CULL_GROUP 4
 #endif
 __device__ __forceinline__ void cull_boxes(const RenderParams &p, const CullRay &c, uint32_t base, uint32_t count,
-                                           unsigned long long &okm, unsigned long long &failm) {
+                                           uint32_t &okm, uint32_t &failm) {
 #pragma unroll 1
     for (uint32_t g = 0; g < count; g += WAVE2_CULL_GROUP) {
         uint32_t ok = 0, fail = 0;
@@ -174,19 +174,14 @@ __device__ __forceinline__ void cull_boxes(const RenderParams &p, const CullRay 
             if (sgap > c.e2) ok |= 1u << j;
             if (sgap < -c.e2) fail |= 1u << j;
         }
-        okm |= (unsigned long long)ok << g;
-        failm |= (unsigned long long)fail << g;
+        okm |= ok << g;
+        failm |= fail << g;
     }
 }
 
 // (A/B'd and rejected, r1: prefetch.global.L1 of the hemisphere / lobe sample at classification time and of the next
 // window of camera samples — 6 % slower at both 4096 and 16384 spp; the loads' latency is already covered by the
 // other resident CTAs.)
-
-// packed per-kind counters for the block scan: 16 bits each (matte | specular | glossy | terminated)
-__device__ __forceinline__ unsigned long long kind_one(uint32_t kind) {
-    return kind == K_NONE ? 0ull : (1ull << (16 * (kind - 1)));
-}
 
 struct SphereScan {
     double A4;      // 4.0 * a, shapes.rs:180
@@ -195,40 +190,39 @@ struct SphereScan {
     uint32_t best_ref;
 };
 
-// Spheres [64 PASS, 64 PASS + 64): FP32 classification of every box, exact BoundingBox::hit (shapes.rs:98-133) for
-// the boxes FP32 could not decide, then the quadratics of the passing spheres in shape order (shapes.rs:176-212).
-template <int PASS, bool COUNT>
-__device__ __forceinline__ void sphere_pass(const RenderParams &p, const double *sph, const CullRay &c, uint32_t ns, V3 o, V3 d,
-                                            SphereScan &sc, unsigned long long *cn) {
-    constexpr int B = 64 * PASS;
-    const uint32_t nsb = ns - B < 64u ? ns - B : 64u;   // spheres in this pass (ns > B)
-    unsigned long long okm = 0ull, failm = 0ull;
-    cull_boxes(p, c, B, nsb, okm, failm);
-    const unsigned long long valid = nsb >= 64 ? ~0ull : ((1ull << nsb) - 1ull);
-    unsigned long long mask = okm & valid;
-    unsigned long long unc = ~(okm | failm) & valid;
+// Spheres [base, base + 32): FP32 classification of every box, exact BoundingBox::hit (shapes.rs:98-133) for the
+// boxes FP32 could not decide, then the quadratics of the passing spheres in shape order (shapes.rs:176-212).
+template <bool COUNT>
+__device__ __forceinline__ void sphere_pass(const RenderParams &p, const double *sph, const CullRay &c, uint32_t base, uint32_t ns,
+                                            V3 o, V3 d, SphereScan &sc, unsigned long long *cn) {
+    const uint32_t nsb = ns - base < 32u ? ns - base : 32u;   // spheres in this pass
+    uint32_t okm = 0u, failm = 0u;
+    cull_boxes(p, c, base, nsb, okm, failm);
+    const uint32_t valid = nsb >= 32u ? ~0u : ((1u << nsb) - 1u);
+    uint32_t mask = okm & valid;
+    uint32_t unc = ~(okm | failm) & valid;
     while (unc) {
         // the exact reciprocals (shapes.rs:107,114,121) are needed on this rare path only
         const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
         const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
-        const uint32_t j = (uint32_t)__ffsll((long long)unc) - 1u;
-        unc &= unc - 1ull;
-        const double *s = sph + (size_t)(B + j) * V_SPH_STRIDE;
+        const uint32_t j = (uint32_t)__ffs((int)unc) - 1u;
+        unc &= unc - 1u;
+        const double *s = sph + (size_t)(base + j) * V_SPH_STRIDE;
         const double tx_min = (s[V_C0X + sx] - o.x) * ia, tx_max = (s[V_C1X - sx] - o.x) * ia;
         const double ty_min = (s[V_C0Y + sy] - o.y) * ib, ty_max = (s[V_C1Y - sy] - o.y) * ib;
         const double tz_min = (s[V_C0Z + sz] - o.z) * ic, tz_max = (s[V_C1Z - sz] - o.z) * ic;
         const double t0 = ref_max(tx_min, ref_max(ty_min, tz_min));
         const double t1 = ref_min(tx_max, ref_min(ty_max, tz_max));
-        if (t0 < t1 && t1 > FLUX_T_MIN) mask |= 1ull << j;
+        if (t0 < t1 && t1 > FLUX_T_MIN) mask |= 1u << j;
     }
     if (COUNT) {
         cn[CN_BBOX_TESTS] += nsb;
-        cn[CN_BBOX_PASS] += __popcll(mask);
+        cn[CN_BBOX_PASS] += __popc(mask);
     }
     while (mask) {
-        const uint32_t j = (uint32_t)__ffsll((long long)mask) - 1u;
-        mask &= mask - 1ull;
-        const double *s = sph + (size_t)(B + j) * V_SPH_STRIDE;
+        const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const double *s = sph + (size_t)(base + j) * V_SPH_STRIDE;
         const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
         const double b = 2.0 * dot3(temp, d);
         const double cc = dot3(temp, temp) - s[V_RR];
@@ -246,13 +240,12 @@ __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double 
         // spheres arrive in shape order: a later one wins only if strictly closer (common.rs:17-23 + min_by)
         if (sc.best_ref == 0xFFFFFFFFu || t < sc.best_t) {
             sc.best_t = t;
-            sc.best_ref = B + j;
+            sc.best_ref = base + j;
         }
     }
 }
 
-// BIG: more than 64 spheres (second sphere pass); a separate instantiation so that the common case keeps its registers
-template <bool COUNT, bool BIG>
+template <bool COUNT>
 __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t ns = p.scene.n_spheres, np = p.scene.n_planes, nm = p.scene.n_materials;
@@ -355,8 +348,8 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     sc.rA2 = rcp_prepare(2.0 * A);
                     sc.best_t = 0.0;
                     sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
-                    sphere_pass<0, COUNT>(p, w.sph, c, ns, o, d, sc, cn);
-                    if (BIG && ns > 64) sphere_pass<1, COUNT>(p, w.sph, c, ns, o, d, sc, cn);
+#pragma unroll 1
+                    for (uint32_t base = 0; base < ns; base += 32) sphere_pass<COUNT>(p, w.sph, c, base, ns, o, d, sc, cn);
                     double best_t = sc.best_t;
                     uint32_t best_ref = sc.best_ref;
                     // ---- planes (shapes.rs:137-139) ----
@@ -416,37 +409,37 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
             }
 
             // ======================= 2: bin the slots by kind (one packed scan) =======================
-            unsigned long long tot, ex;
+            // per-warp counts travel as two packed words (matte | specular << 16, glossy | terminated << 16); after the
+            // barrier lanes 0..7 of every warp scan the 8 warp totals with three shuffle steps
+            uint32_t n_matte, n_spec, n_gloss, n_term, pos;
             {
                 const uint32_t bm = __ballot_sync(0xffffffffu, kind == K_MATTE);
                 const uint32_t bs = __ballot_sync(0xffffffffu, kind == K_SPEC);
                 const uint32_t bg = __ballot_sync(0xffffffffu, kind == K_GLOSSY);
                 const uint32_t bt = __ballot_sync(0xffffffffu, kind == K_TERM);
-                unsigned long long *scr = w.scr + (WAVE2_S / 32) * (rot++ & 1u);
-                if (lane == 0)
-                    scr[warp] = (unsigned long long)__popc(bm) | ((unsigned long long)__popc(bs) << 16) |
-                                ((unsigned long long)__popc(bg) << 32) | ((unsigned long long)__popc(bt) << 48);
+                uint2 *scr = reinterpret_cast<uint2 *>(w.scr) + (WAVE2_S / 32) * (rot++ & 1u);
+                if (lane == 0) scr[warp] = make_uint2(__popc(bm) | (__popc(bs) << 16), __popc(bg) | (__popc(bt) << 16));
                 const uint32_t mine = kind == K_MATTE ? bm : (kind == K_SPEC ? bs : (kind == K_GLOSSY ? bg : bt));
                 const uint32_t rank = __popc(mine & lt_mask);
                 __syncthreads();
-                unsigned long long base = 0;
-                tot = 0;
+                uint2 inc = lane < WAVE2_S / 32 ? scr[lane] : make_uint2(0u, 0u);
+                const uint2 own = inc;
 #pragma unroll
-                for (uint32_t q = 0; q < WAVE2_S / 32; q++) {
-                    const unsigned long long c = scr[q];
-                    if (q < warp) base += c;
-                    tot += c;
+                for (uint32_t st = 1; st < WAVE2_S / 32; st <<= 1) {
+                    const uint32_t ux = __shfl_up_sync(0xffffffffu, inc.x, st), uy = __shfl_up_sync(0xffffffffu, inc.y, st);
+                    if (lane >= st) { inc.x += ux; inc.y += uy; }
                 }
-                ex = base + (unsigned long long)rank * kind_one(kind);
+                const uint32_t tx = __shfl_sync(0xffffffffu, inc.x, WAVE2_S / 32 - 1), ty = __shfl_sync(0xffffffffu, inc.y, WAVE2_S / 32 - 1);
+                const uint32_t bx = __shfl_sync(0xffffffffu, inc.x - own.x, warp), by = __shfl_sync(0xffffffffu, inc.y - own.y, warp);
+                n_matte = tx & 0xFFFFu; n_spec = tx >> 16; n_gloss = ty & 0xFFFFu; n_term = ty >> 16;
+                pos = rank + (kind == K_MATTE ? (bx & 0xFFFFu)
+                              : kind == K_SPEC ? n_matte + (bx >> 16)
+                              : kind == K_GLOSSY ? n_matte + n_spec + (by & 0xFFFFu)
+                                                 : n_matte + n_spec + n_gloss + (by >> 16));
             }
-            const uint32_t n_matte = (uint32_t)(tot & 0xFFFFu), n_spec = (uint32_t)((tot >> 16) & 0xFFFFu);
-            const uint32_t n_gloss = (uint32_t)((tot >> 32) & 0xFFFFu), n_term = (uint32_t)((tot >> 48) & 0xFFFFu);
             const uint32_t n_items = n_matte + n_spec + n_gloss + n_term;
             if (n_items == 0) break;   // every slot idle (uniform)
-            if (kind == K_MATTE) w.list[(uint32_t)(ex & 0xFFFFu)] = tid;
-            else if (kind == K_SPEC) w.list[n_matte + (uint32_t)((ex >> 16) & 0xFFFFu)] = tid;
-            else if (kind == K_GLOSSY) w.list[n_matte + n_spec + (uint32_t)((ex >> 32) & 0xFFFFu)] = tid;
-            else if (kind == K_TERM) w.list[n_matte + n_spec + n_gloss + (uint32_t)((ex >> 48) & 0xFFFFu)] = tid;
+            if (kind != K_NONE) w.list[pos] = tid;
             __syncthreads();
 
             // ======================= 3: one thread per item, in kind order =======================
@@ -590,16 +583,11 @@ void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaSt
     const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;
     const uint64_t cap = (uint64_t)sm_count * WAVE2_MIN_BLOCKS;
     const int blocks = (int)(npix < cap ? (npix ? npix : 1) : cap);
-    const bool big = p.scene.n_spheres > 64;
-    auto go = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<blocks, WAVE2_S, smem, stream>>>(p);
-    };
     if (count) {
-        if (big) go(render_wave2_kernel<true, true>);
-        else go(render_wave2_kernel<true, false>);
+        cudaFuncSetAttribute(render_wave2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_wave2_kernel<true><<<blocks, WAVE2_S, smem, stream>>>(p);
     } else {
-        if (big) go(render_wave2_kernel<false, true>);
-        else go(render_wave2_kernel<false, false>);
+        cudaFuncSetAttribute(render_wave2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        render_wave2_kernel<false><<<blocks, WAVE2_S, smem, stream>>>(p);
     }
 }
