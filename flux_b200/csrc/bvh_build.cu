@@ -72,9 +72,13 @@ struct Builder {
     void set_child(uint32_t node, int slot, uint32_t ref, const Box &bx) {
         BvhNode4 &n = out->nodes[node];
         n.child[slot] = ref;
-        for (int k = 0; k < 3; k++) {
-            n.lo[k][slot] = bx.lo[k] - pad;
-            n.hi[k][slot] = bx.hi[k] + pad;
+        for (int k = 0; k < 3; k++) {   // padded in f64, then rounded OUTWARD to f32
+            const double lo = bx.lo[k] - pad, hi = bx.hi[k] + pad;
+            float flo = (float)lo, fhi = (float)hi;
+            if ((double)flo > lo) flo = std::nextafter(flo, -std::numeric_limits<float>::infinity());
+            if ((double)fhi < hi) fhi = std::nextafter(fhi, std::numeric_limits<float>::infinity());
+            n.lo[k][slot] = flo;
+            n.hi[k][slot] = fhi;
         }
     }
     // builds the subtree over [a,b) (b - a > leaf_size) and returns its node index; level = depth of this node
@@ -87,11 +91,11 @@ struct Builder {
             for (int s = 0; s < 4; s++) {
                 n.child[s] = BVH_EMPTY;
                 for (int k = 0; k < 3; k++) {
-                    n.lo[k][s] = std::numeric_limits<double>::infinity();
-                    n.hi[k][s] = -std::numeric_limits<double>::infinity();
+                    n.lo[k][s] = std::numeric_limits<float>::infinity();
+                    n.hi[k][s] = -std::numeric_limits<float>::infinity();
                 }
             }
-            for (int s = 0; s < 12; s++) n.pad[s] = 0;
+            for (int s = 0; s < 4; s++) n.pad[s] = 0;
         }
         uint32_t cut[5];
         cut[0] = a;
@@ -257,9 +261,9 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
             BvhNode4 &r = out.nodes[0];
             for (int s = 0; s < 4; s++) {
                 r.child[s] = BVH_EMPTY;
-                for (int k = 0; k < 3; k++) r.lo[k][s] = std::numeric_limits<double>::infinity(), r.hi[k][s] = -r.lo[k][s];
+                for (int k = 0; k < 3; k++) r.lo[k][s] = std::numeric_limits<float>::infinity(), r.hi[k][s] = -r.lo[k][s];
             }
-            for (int s = 0; s < 12; s++) r.pad[s] = 0;
+            for (int s = 0; s < 4; s++) r.pad[s] = 0;
             out.depth = 1;
             B.set_child(0, 0, B.make_leaf(0, (uint32_t)n), B.bounds(0, (uint32_t)n));
         } else {

@@ -19,11 +19,22 @@
 // Planes are unbounded and a few very large spheres (environment spheres) would bloat the top of the
 // tree: both are kept in a linear list that is tested before the traversal.
 //
-// Layout: BvhNode4 is 256 B (two 128 B lines), child boxes SoA so that one double2 load serves two
-// children; a child reference is an inner node index, a leaf (offset, count) into bvh_prims, or EMPTY.
-// Leaf primitives are fetched from 128 B / 80 B array-of-structure records (one or two lines per
-// primitive) instead of the 12 strided planes of the linear-scan SoA.
+// Node boxes are stored and tested in FP32 — conservatively: the builder rounds the (padded) f64 child boxes outward
+// to f32, the traversal forms each slab value as fma(c, 1/d, -(o/d)) in f32 with the operand -(o/d) lowered (entry)
+// or raised (exit) by a per-axis bound E_k >= the f32 evaluation error (same derivation as the box classification
+// of render_wave2.cu), so the f32 entry distance never exceeds and the f32 exit distance never falls below the
+// value the reference's f64 expression would give for the same box.  A node is skipped only on those one-sided
+// bounds; zero / denormal direction components use a clamped reciprocal of magnitude 1e30 with the sign of d_k
+// (a box containing o_k on that axis then imposes no constraint, one not containing it is missed — what 1/0 = inf
+// does in the reference), non-finite rays cull nothing.  Leaves run the exact f64 primitive tests.
+//
+// Layout: BvhNode4 is 128 B (one line): child boxes SoA (float4 per axis and bound), 4 child references; a child
+// reference is an inner node index, a leaf (offset, count) into bvh_prims, or EMPTY.  Leaf primitives are fetched
+// from 112 B / 96 B array-of-structure records (one or two lines per primitive) instead of the 12 strided planes
+// of the linear-scan SoA.
 #pragma once
+#include <math_constants.h>
+
 #include "flux_intersect.cuh"
 
 #define BVH_EMPTY 0xFFFFFFFFu
@@ -32,13 +43,13 @@
 #define BVH_PAD_REL 1e-7
 #define BVH_PRUNE_REL 1e-9
 
-struct __align__(256) BvhNode4 {
-    double lo[3][4];     // [axis][child]
-    double hi[3][4];
+struct __align__(128) BvhNode4 {
+    float lo[3][4];      // [axis][child], rounded down
+    float hi[3][4];      // rounded up
     uint32_t child[4];   // EMPTY | inner node index | LEAF | offset << 3 | (count - 1)
-    uint32_t pad[12];
+    uint32_t pad[4];
 };
-static_assert(sizeof(BvhNode4) == 256, "BvhNode4 layout");
+static_assert(sizeof(BvhNode4) == 128, "BvhNode4 layout");
 
 // leaf records
 struct __align__(16) SphRec {   // 112 B
@@ -139,57 +150,72 @@ __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayC
     const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
     const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
     const TriRec *__restrict__ trec = reinterpret_cast<const TriRec *>(sc.bvh_tri);
+    // ---- f32 ray constants: near = fma(c_near, ia, nlo) <= exact entry, far = fma(c_far, ia, nhi) >= exact exit ----
+    float ia32[3], nlo[3], nhi[3];
+    bool pos[3];
+    {
+        const double dd[3] = {r.d.x, r.d.y, r.d.z}, oo[3] = {r.o.x, r.o.y, r.o.z};
+        const float ext = __double2float_ru(sc.bvh_extent);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float df = (float)dd[k], of = (float)oo[k];
+            float a;
+            asm("rcp.approx.f32 %0, %1;" : "=f"(a) : "f"(df));   // max relative error 2^-23; 1/+-0 = +-inf
+            if (!(fabsf(a) < 1e30f)) a = copysignf(1e30f, df);
+            const float noa = -(of * a);
+            // |f32 slab - exact slab| <= (2^-22 + 2^-23)(|c| + |o|)|ia| + 2^-24 |slab| <= E
+            const float E = fabsf(a) * (ext + fabsf(of)) * (1.01f * 9.5367431640625e-07f);
+            const bool sane = (df == df) && (fabsf(noa) < 1e37f) && (E < 1e37f);
+            pos[k] = !signbit(a);                 // = (1/d_k >= 0) of BoundingBox::hit, shapes.rs:108,115,122
+            ia32[k] = sane ? a : 0.0f;
+            nlo[k] = sane ? noa - E : -CUDART_INF_F;   // an axis that cannot be bounded constrains nothing
+            nhi[k] = sane ? noa + E : CUDART_INF_F;
+        }
+    }
+    float t_prune32 = CUDART_INF_F;   // >= t_prune, refreshed lazily
+    double t_prune_seen = inf;
     uint32_t sp = 0;
     uint32_t cur = 0;  // root
     for (;;) {
         if (!(cur & BVH_LEAF)) {
             if (COUNT) cn[CN_NODES]++;
+            if (t_prune != t_prune_seen) {
+                t_prune_seen = t_prune;
+                t_prune32 = __double2float_ru(t_prune);
+            }
             const BvhNode4 *nd = nodes + cur;
-            // near/far corner per axis by the sign test of BoundingBox::hit (shapes.rs:108,115,122)
-            const double *nx = r.pa ? nd->lo[0] : nd->hi[0], *fx = r.pa ? nd->hi[0] : nd->lo[0];
-            const double *ny = r.pb ? nd->lo[1] : nd->hi[1], *fy = r.pb ? nd->hi[1] : nd->lo[1];
-            const double *nz = r.pc ? nd->lo[2] : nd->hi[2], *fz = r.pc ? nd->hi[2] : nd->lo[2];
+            const float4 *lo4 = reinterpret_cast<const float4 *>(nd->lo), *hi4 = reinterpret_cast<const float4 *>(nd->hi);
+            const float4 ax = __ldg(pos[0] ? lo4 + 0 : hi4 + 0), bx = __ldg(pos[0] ? hi4 + 0 : lo4 + 0);
+            const float4 ay = __ldg(pos[1] ? lo4 + 1 : hi4 + 1), by = __ldg(pos[1] ? hi4 + 1 : lo4 + 1);
+            const float4 az = __ldg(pos[2] ? lo4 + 2 : hi4 + 2), bz = __ldg(pos[2] ? hi4 + 2 : lo4 + 2);
             const uint4 ch = __ldg(reinterpret_cast<const uint4 *>(nd->child));
-            double t0[4];
+            float key[4];
             uint32_t ref[4];
             ref[0] = ch.x; ref[1] = ch.y; ref[2] = ch.z; ref[3] = ch.w;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const double2 ax = ldg2(nx + 2 * h), bx = ldg2(fx + 2 * h);
-                const double2 ay = ldg2(ny + 2 * h), by = ldg2(fy + 2 * h);
-                const double2 az = ldg2(nz + 2 * h), bz = ldg2(fz + 2 * h);
-                {
-                    const double tn = fmax(fmax((ax.x - r.o.x) * r.ia, (ay.x - r.o.y) * r.ib), (az.x - r.o.z) * r.ic);
-                    const double tf = fmin(fmin((bx.x - r.o.x) * r.ia, (by.x - r.o.y) * r.ib), (bz.x - r.o.z) * r.ic);
-                    const bool skip = (tn >= tf) || (tf <= FLUX_T_MIN) || (tn > t_prune);
-                    t0[2 * h] = tn;
-                    if (skip) ref[2 * h] = BVH_EMPTY;
-                }
-                {
-                    const double tn = fmax(fmax((ax.y - r.o.x) * r.ia, (ay.y - r.o.y) * r.ib), (az.y - r.o.z) * r.ic);
-                    const double tf = fmin(fmin((bx.y - r.o.x) * r.ia, (by.y - r.o.y) * r.ib), (bz.y - r.o.z) * r.ic);
-                    const bool skip = (tn >= tf) || (tf <= FLUX_T_MIN) || (tn > t_prune);
-                    t0[2 * h + 1] = tn;
-                    if (skip) ref[2 * h + 1] = BVH_EMPTY;
-                }
-            }
-            // order: EMPTY last, then by entry distance (NaN entry = unknown = nearest); 5-comparator network
-#define BVH_KEY(k) (ref[k] == BVH_EMPTY ? inf : (t0[k] == t0[k] ? t0[k] : -inf))
-            double key[4] = {BVH_KEY(0), BVH_KEY(1), BVH_KEY(2), BVH_KEY(3)};
+#define BVH_CHILD(k, C)                                                                                             \
+    {                                                                                                               \
+        const float tn = fmaxf(fmaxf(fmaf(ax.C, ia32[0], nlo[0]), fmaf(ay.C, ia32[1], nlo[1])), fmaf(az.C, ia32[2], nlo[2])); \
+        const float tf = fminf(fminf(fmaf(bx.C, ia32[0], nhi[0]), fmaf(by.C, ia32[1], nhi[1])), fmaf(bz.C, ia32[2], nhi[2])); \
+        /* fmaxf / fminf drop NaN slabs (inf * 0): they constrain nothing; every comparison is false for NaN */    \
+        const bool skip = (tn > tf) || (tf < 0.000499f) || (tn > t_prune32);                                       \
+        if (skip) ref[k] = BVH_EMPTY;                                                                               \
+        key[k] = ref[k] == BVH_EMPTY ? CUDART_INF_F : (tn == tn ? tn : -CUDART_INF_F);                              \
+    }
+            BVH_CHILD(0, x) BVH_CHILD(1, y) BVH_CHILD(2, z) BVH_CHILD(3, w)
+#undef BVH_CHILD
+            // order: EMPTY last, then by entry bound (unknown = nearest); 5-comparator network
 #define BVH_CSWAP(a, b)                                                         \
     if (key[b] < key[a]) {                                                      \
-        const double tk = key[a]; key[a] = key[b]; key[b] = tk;                 \
+        const float tk = key[a]; key[a] = key[b]; key[b] = tk;                  \
         const uint32_t tr = ref[a]; ref[a] = ref[b]; ref[b] = tr;               \
     }
             BVH_CSWAP(0, 1) BVH_CSWAP(2, 3) BVH_CSWAP(0, 2) BVH_CSWAP(1, 3) BVH_CSWAP(1, 2)
 #undef BVH_CSWAP
-#undef BVH_KEY
             // push far children first so that the nearest is popped first; continue with the nearest
 #pragma unroll
             for (int k = 3; k >= 1; k--)
                 if (ref[k] != BVH_EMPTY) {
-                    // entry distance rounded DOWN to f32: a conservative re-test when popped
-                    stack[(size_t)sp * stride] = make_uint2(ref[k], __float_as_uint(__double2float_rd(key[k])));
+                    stack[(size_t)sp * stride] = make_uint2(ref[k], __float_as_uint(key[k]));   // entry bound: re-tested when popped
                     sp++;
                 }
             if (ref[0] != BVH_EMPTY) {
