@@ -617,7 +617,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
         return fail(ctx, FLUX_ERR_INVALID, "render: wavefront kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
     const bool wave2_ok = wave2_kernel_applicable(p);
     if (ctx->kernel_mode == 4 && !wave2_ok)
-        return fail(ctx, FLUX_ERR_INVALID, "render: wavefront-2 kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
+        return fail(ctx, FLUX_ERR_INVALID, "render: wavefront-2 kernel needs spp >= 256, depth <= 8 and a sphere/plane scene of at most 128 spheres");
     if (wave2_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 4))
         launch_render_wave2(p, ctx->count, ctx->sm_count, st);
     else if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))

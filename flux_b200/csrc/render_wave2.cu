@@ -43,6 +43,10 @@
 #define WAVE2_MIN_BLOCKS (1024 / WAVE2_S)   // 64 registers per thread: 32 warps per SM
 #endif
 #define WAVE2_MAX_DEPTH 8    // deeper jobs use the other kernels
+#ifndef WAVE2_MIN_SPP
+#define WAVE2_MIN_SPP 256    // measured r1 (demo2): 4.63 / 5.18 / 5.99 / 6.44 / 6.96 Gsamples/s at 256 / 529 / 1024 / 2025 /
+                             // 16384 spp against 4.5-4.7 for the regeneration kernel; below 256 the per-pixel drain tail wins
+#endif
 
 namespace {
 
@@ -570,10 +574,10 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 
 }  // namespace
 
-// Applies when a CTA can own a pixel (spp >= 4096 keeps the per-pixel drain tail under ~2 %), the scene has only
+// Applies when a CTA can own a pixel (spp >= 256; the per-pixel drain tail is ~2 % at 16384 spp), the scene has only
 // spheres and planes, at most FLUX_CULL_MAX = 128 spheres / 255 materials, and depth <= 8.
 bool wave2_kernel_applicable(const RenderParams &p) {
-    return p.ss.n >= 4096 && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= FLUX_CULL_MAX &&
+    return p.ss.n >= WAVE2_MIN_SPP && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= FLUX_CULL_MAX &&
            p.scene.n_materials <= 255 && p.cam.max_depth >= 1 && p.cam.max_depth <= WAVE2_MAX_DEPTH &&
            w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth) <= (size_t)(226 * 1024) / 3 - 1024;   // at least 3 CTAs per SM
 }

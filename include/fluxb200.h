@@ -252,7 +252,7 @@ int flux_bvh_describe(const flux_scene_flat *scene, uint64_t out[8]);
  * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene),
  * 3 = block-local wavefront (CTA per pixel, compacted candidate pairs, material-sorted shading;
  * needs spp >= 4096, depth <= 8), 4 = second-generation wavefront (same slot/sample schedule and output bits
- * as 3; conservative FP32 box pre-test, sorted regeneration; the auto choice when it applies).  All compute the
+ * as 3; conservative FP32 box pre-test, sorted regeneration; needs spp >= 256; the auto choice when it applies).  All compute the
  * same per-sample radiance; they differ only in the order of the per-pixel sum (last bits).  Used by parity
  * tests and A/B timing. */
 int flux_set_kernel_mode(flux_ctx *ctx, int mode);
