@@ -243,7 +243,7 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
     // ---- leaf size: smallest in {4, 8} whose (balanced) tree fits the traversal stack ----
     const uint64_t n = B.items.size();
     const std::vector<Item> pristine = B.items;
-    for (uint32_t leaf = 4;; leaf *= 2) {
+    for (uint32_t leaf = BVH_FIRST_LEAF;; leaf *= 2) {
         if (leaf > 8) {
             err = "bvh: tree depth " + std::to_string(out.depth) + " exceeds the traversal stack (scene too large)";
             return false;

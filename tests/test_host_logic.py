@@ -130,7 +130,7 @@ def test_bvh_builder_invariants_sphere_cloud():
     d = _describe(flat)
     assert d["violations"] == 0 and d["miscount"] == 0
     assert d["refs"] + d["linear"] == 10_000 and d["linear"] == 0
-    assert d["auto"] == 1 and 3 * d["levels"] + 1 <= 32 and d["leaf"] == 4
+    assert d["auto"] == 1 and 3 * d["levels"] + 1 <= 32 and d["leaf"] == 2
     assert d["nodes"] < 10_000 // 2
 
 
