@@ -611,7 +611,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     CK(cudaEventRecord(ctx->ev0, st));
     const bool regen_ok = regen_kernel_applicable(p);
     if (ctx->kernel_mode == 2 && !regen_ok)
-        return fail(ctx, FLUX_ERR_INVALID, "render: regeneration kernel needs spp >= 64 and a sphere/plane scene that fits shared memory");
+        return fail(ctx, FLUX_ERR_INVALID, "render: regeneration kernel needs spp >= 64 and a BVH scene or a sphere/plane scene that fits shared memory");
     const bool wave_ok = wave_kernel_applicable(p);
     if (ctx->kernel_mode == 3 && !wave_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: wavefront kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");

@@ -21,6 +21,7 @@
 // The scene (spheres, planes, materials) is staged once per CTA into shared
 // memory as AoS records; bounding-box corners are addressed through per-ray
 // near/far offsets so the slab test needs no selects.
+#include "flux_bvh.cuh"
 #include "flux_intersect.cuh"
 #include "flux_kernels.cuh"
 #include "flux_shade.cuh"
@@ -181,11 +182,14 @@ __device__ __forceinline__ void closest_hit_smem(const SmemScene &sc, V3 o, V3 d
     }
 }
 
-template <bool COUNT>
+// BVH = true: closest hit through the 4-wide BVH over the scene in global memory (meshes, many spheres) instead of
+// the shared-memory linear scan; shared memory then holds the per-thread traversal stacks.
+template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *bvh_stack = reinterpret_cast<uint2 *>(smem_raw) + threadIdx.x;   // [BVH_STACK][blockDim.x] when BVH
     // ---- stage the scene into shared memory (once per CTA) ----
-    const uint32_t ns = p.scene.n_spheres, np = p.scene.n_planes, nm = p.scene.n_materials;
+    const uint32_t ns = BVH ? 0u : p.scene.n_spheres, np = BVH ? 0u : p.scene.n_planes, nm = BVH ? 0u : p.scene.n_materials;
     double *s_sph = reinterpret_cast<double *>(smem_raw);
     double *s_pln = s_sph + (size_t)ns * R_SPH_STRIDE;
     DevMaterial *s_mat = reinterpret_cast<DevMaterial *>(s_pln + (size_t)np * R_PLN_STRIDE);
@@ -289,9 +293,18 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                 term = true;
             } else {
                 if (COUNT) cn[CN_SEGMENTS]++;
-                double t;
-                uint32_t hid, href;
-                closest_hit_smem<COUNT>(sc, o, d, t, hid, href, cn);
+                double t = 0.0;
+                uint32_t hid, href = 0;
+                RayCtx rc;
+                HitRef href_bvh;
+                if (BVH) {
+                    rc = make_ray(o, d);
+                    href_bvh = closest_hit_bvh<COUNT>(p.scene, rc, bvh_stack, blockDim.x, cn);
+                    hid = href_bvh.shape_id;
+                    t = href_bvh.t;
+                } else {
+                    closest_hit_smem<COUNT>(sc, o, d, t, hid, href, cn);
+                }
                 if (hid == 0xFFFFFFFFu) {  // scene.rs:168
                     if (COUNT) cn[CN_MISS]++;
                     L = Rgb{cam.bg[0], cam.bg[1], cam.bg[2]};
@@ -300,21 +313,29 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                     // hit record of the closest hit only (shapes.rs:140-147,191-198)
                     V3 normal;
                     uint32_t mi;
-                    const V3 point = o + t * d;
-                    if (href & 0x80000000u) {
+                    V3 point;
+                    if (BVH) {
+                        const HitRec hrec = build_hit(p.scene, rc, href_bvh);
+                        normal = hrec.normal;
+                        point = hrec.point;
+                        mi = hrec.material;
+                        if (COUNT) cn[href_bvh.kind == KIND_SPHERE ? CN_HIT_SPHERE : (href_bvh.kind == KIND_PLANE ? CN_HIT_PLANE : CN_HIT_TRI)]++;
+                    } else if (href & 0x80000000u) {
+                        point = o + t * d;
                         const uint32_t k = href & 0x7FFFFFFFu;
                         const double *pl = sc.pln + (size_t)k * R_PLN_STRIDE;
                         normal = mk3(pl[R_PNX], pl[R_PNY], pl[R_PNZ]);
                         mi = sc.pln_mat[k];
                         if (COUNT) cn[CN_HIT_PLANE]++;
                     } else {
+                        point = o + t * d;
                         const double *s = sc.sph + (size_t)href * R_SPH_STRIDE;
                         const V3 temp = mk3(o.x - s[R_CX], o.y - s[R_CY], o.z - s[R_CZ]);
                         normal = ((temp + t * d) * s[R_INV]) / s[R_R];
                         mi = sc.sph_mat[href];
                         if (COUNT) cn[CN_HIT_SPHERE]++;
                     }
-                    const DevMaterial &m = sc.mat[mi];
+                    const DevMaterial &m = BVH ? p.scene.materials[mi] : sc.mat[mi];
                     const uint32_t kind = m.kind;
                     double c0 = m.c[0], c1 = m.c[1], c2 = m.c[2];
                     if (kind == FLUX_MAT_EMISSIVE) {  // materials.rs:42-49
@@ -400,6 +421,7 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
 }
 
 size_t regen_smem_bytes(const DevScene &sc) {
+    if (sc.use_bvh) return (size_t)BVH_STACK * REGEN_THREADS * sizeof(uint2);   // per-thread traversal stacks
     size_t b = (size_t)sc.n_spheres * R_SPH_STRIDE * 8 + (size_t)sc.n_planes * R_PLN_STRIDE * 8 +
                (size_t)sc.n_materials * sizeof(DevMaterial) + (size_t)(2 * sc.n_spheres + 2 * sc.n_planes) * 4;
     return align_up(b, 16);
@@ -407,11 +429,13 @@ size_t regen_smem_bytes(const DevScene &sc) {
 
 }  // namespace
 
-// The regeneration kernel applies when a warp can own a pixel (spp >= 64), the scene has only
-// spheres and planes, and it fits in shared memory next to two CTAs per SM.
+// The regeneration kernel applies when a warp can own a pixel (spp >= 64) and either the scene goes through the
+// BVH (meshes, more than 40 bounded shapes) or it has only spheres and planes and fits in shared memory next to
+// two CTAs per SM.
 bool regen_kernel_applicable(const RenderParams &p) {
-    return p.ss.n >= 64 && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= 64 &&
-           regen_smem_bytes(p.scene) <= 96 * 1024;
+    if (p.ss.n < 64) return false;
+    if (p.scene.use_bvh) return true;
+    return p.scene.n_tris == 0 && p.scene.n_spheres <= 64 && regen_smem_bytes(p.scene) <= 96 * 1024;
 }
 
 void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
@@ -421,11 +445,16 @@ void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaSt
     uint64_t want = (npix + (threads / 32) - 1) / (threads / 32);
     uint64_t cap = (uint64_t)sm_count * REGEN_MIN_BLOCKS;
     int blocks = (int)(want < cap ? (want ? want : 1) : cap);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, threads, smem, stream>>>(p);
+    };
+    const bool bvh = p.scene.use_bvh != 0;
     if (count) {
-        cudaFuncSetAttribute(render_regen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_regen_kernel<true><<<blocks, threads, smem, stream>>>(p);
+        if (bvh) go(render_regen_kernel<true, true>);
+        else go(render_regen_kernel<true, false>);
     } else {
-        cudaFuncSetAttribute(render_regen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_regen_kernel<false><<<blocks, threads, smem, stream>>>(p);
+        if (bvh) go(render_regen_kernel<false, true>);
+        else go(render_regen_kernel<false, false>);
     }
 }

@@ -168,3 +168,32 @@ def test_full_size_mesh_bvh_vs_linear_on_gpu(gpu_ctx):
     _same(bvh, lin)
     assert (bvh[0] >= 2).mean() > 0.4   # a good share of the rays land on the mesh
     assert (bvh[0] >= 0).all()          # the rest on the environment sphere
+
+
+def test_mesh_scene_regeneration_kernel_with_bvh(gpu_ctx):
+    """spp >= 64 on a BVH scene selects the regeneration kernel with BVH traversal (warp per pixel, in-warp path
+    regeneration): must agree with the oracle's linear scan and with the direct BVH kernel's counters."""
+    sd = synth.mesh_scene(40, 24, seed=3, width=32, height=24)
+    cfg = JobConfiguration(8, 5, 50)
+    ss = Hp.oracle_samples(9, cfg, 32, 24)
+    flat = sd.flatten()
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    imgs, cns = {}, {}
+    try:
+        for mode in (1, 2):   # direct, regeneration — both through the BVH (1922 shapes)
+            gpu_ctx.set_kernel_mode(mode)
+            gpu_ctx.enable_counters(True)
+            gpu_ctx.reset_counters()
+            imgs[mode] = gpu_ctx.render_rows(0, 23, 32)
+            cns[mode] = gpu_ctx.counters()
+            gpu_ctx.enable_counters(False)
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.enable_counters(False)
+    ref = O.render_rows(flat, cfg, ss, 0, 23)
+    assert Hp.rel_err(imgs[1], ref) <= 1e-12
+    assert Hp.rel_err(imgs[2], ref) <= 1e-12
+    assert cns[1] == cns[2] and cns[2]["nodes_visited"] > 0 and cns[2]["hit_tri"] > 0
+    gpu_ctx.set_kernel_mode(0)
+    auto = gpu_ctx.render_rows(0, 23, 32)
+    assert np.array_equal(auto.view(np.uint64), imgs[2].view(np.uint64))   # auto mode = regeneration kernel here
