@@ -234,12 +234,18 @@ class GpuWorker:
     def info(self) -> dict:  # WorkerInfo, manager.rs:30-33
         return {"name": f"gpu{self.ctx.device}", "num_threads": 1}
 
-    def run_job(self, scene_data: SceneData, config: JobConfiguration, units: Optional[Iterable[WorkUnit]] = None):
+    def run_job(self, scene_data: SceneData, config: JobConfiguration, units: Optional[Iterable[WorkUnit]] = None,
+                cancel=None):
+        """Yields one WorkUnitResult per work unit.  ``cancel`` (a callable returning bool) mirrors
+        JobHandle::cancel / CancellableIterator (manager.rs:66-69,365-393): once it returns True no further unit
+        is issued; units already rendered have been yielded."""
         scene = Scene.from_data(scene_data, config)
         camera = Camera.new(scene, config, scene.output_settings.image_width, seed=self.seed, ctx=self.ctx)
         if units is None:
             units = work_units(scene.output_settings.image_height, config.rows_per_work_unit)
         for unit in units:
+            if cancel is not None and cancel():
+                return
             yield camera.render(scene, unit)
 
     def render_image(self, scene_data: SceneData, config: JobConfiguration) -> np.ndarray:

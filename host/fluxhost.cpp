@@ -668,12 +668,15 @@ WorkerInfo GpuWorker::info() const {
     return WorkerInfo{name, (uint32_t)devices_.size()};
 }
 
-std::vector<WorkUnitResult> GpuWorker::run_job(const SceneData &sd, const JobConfiguration &cfg) {
+std::vector<WorkUnitResult> GpuWorker::run_job(const SceneData &sd, const JobConfiguration &cfg, const std::atomic<bool> *cancel) {
     Scene scene = Scene::from_data(sd, cfg);
     GpuContext &ctx = *contexts_[0];
     Camera camera = Camera::create(ctx, scene, cfg, sd.output_settings.image_width, seed_);
     std::vector<WorkUnitResult> out;
-    for (const WorkUnit &u : work_units(sd.output_settings.image_height, cfg.rows_per_work_unit)) out.push_back(camera.render(scene, u));
+    for (const WorkUnit &u : work_units(sd.output_settings.image_height, cfg.rows_per_work_unit)) {
+        if (cancel && cancel->load()) break;   // stop issuing; nothing is in flight between units
+        out.push_back(camera.render(scene, u));
+    }
     return out;
 }
 

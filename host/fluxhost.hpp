@@ -17,6 +17,7 @@
 // Everything that computes pixels is behind libfluxb200.so; there is no CPU rendering path in this file.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -157,8 +158,10 @@ class GpuWorker {
     WorkerInfo info() const;
     // workers.rs:46-64 for one job: Scene::from_data, Camera::new, render every work unit -> image
     Image render_job(const SceneData &sd, const JobConfiguration &cfg, double *render_seconds = nullptr);
-    // the single-GPU loop body itself, unit by unit (what a manager would drive)
-    std::vector<WorkUnitResult> run_job(const SceneData &sd, const JobConfiguration &cfg);
+    // the single-GPU loop body itself, unit by unit (what a manager would drive).  `cancel` mirrors
+    // JobHandle::cancel / CancellableIterator (manager.rs:66-69,365-393): once set, no further unit is issued; the
+    // unit in flight finishes; the rows rendered so far are returned (missing rows stay black in an Image).
+    std::vector<WorkUnitResult> run_job(const SceneData &sd, const JobConfiguration &cfg, const std::atomic<bool> *cancel = nullptr);
 
   private:
     std::vector<int> devices_;

@@ -441,3 +441,22 @@ def test_wavefront2_divergent_glossy_scene_with_67_spheres(gpu_ctx):
     for k, v in cn_o.items():
         assert abs(cn[k] - v) <= max(2, 1e-6 * v), (k, cn[k], v)
     assert min(cn_o["matte"], cn_o["glossy"], cn_o["specular"], cn_o["emissive"]) > 0
+
+
+def test_worker_cancellation_stops_issuing_units(demo1):
+    """JobHandle::cancel semantics (manager.rs:66-69,365-393): units already rendered are delivered, no further
+    unit is issued; the delivered rows equal an uncancelled render's."""
+    from flux_b200.worker import GpuWorker
+    sd = demo1.with_size(48, 40)
+    cfg = JobConfiguration(2, 5, 8)   # 5 work units of 8 rows
+    w = GpuWorker(0, seed=4)
+    try:
+        full = w.render_image(sd, cfg)
+        got = []
+        for res in w.run_job(sd, cfg, cancel=lambda: len(got) >= 2):
+            got.append(res)
+    finally:
+        w.stop()
+    assert [(r.work_unit.row_start, r.work_unit.row_end) for r in got] == [(0, 7), (8, 15)]
+    for r in got:
+        assert np.array_equal(r.rows.view(np.uint64), full[r.work_unit.row_start:r.work_unit.row_end + 1].view(np.uint64))
