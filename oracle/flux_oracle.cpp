@@ -741,7 +741,7 @@ int oracle_hit_record(const flux_scene_flat *scene, const double *o, const doubl
     Scene s;
     if (!build_scene(scene, 1, s)) return -2;
     Ray r{ld3(o), ld3(d)};
-    Hit h;
+    Hit h{};
     if (!scene_hit(s, r, 1, h, nullptr)) return -1;
     *t = h.distance;
     st3(normal, h.normal);
