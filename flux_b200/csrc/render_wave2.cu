@@ -249,6 +249,16 @@ __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double 
     }
 }
 
+// -DWAVE2_TIMING: per-warp cycle accounting of the stages and barrier waits (lane 0 of every warp, clock64), summed
+// into the event-counter array and read by tools/wave2_timing.py: [0] owner stage, [1] wait at barrier 1, [2] bin,
+// [3] wait at barrier 2, [4] item stage, [5] wait at barrier 3, [6] warp-iterations, [7..14] item-stage time and
+// count by the kind of the warp's first lane (matte, glossy/specular, terminated, idle).  A debugging build only.
+#ifdef WAVE2_TIMING
+#define TMARK(k) { const long long t_now = clock64(); if (lane == 0) t_acc[k] += t_now - t_prev; t_prev = t_now; }
+#else
+#define TMARK(k)
+#endif
+
 template <bool COUNT>
 __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -293,6 +303,9 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
     __shared__ uint32_t s_pixel;
     __shared__ double s_red[3][WAVE2_S / 32];
     uint32_t rot = 0;
+#ifdef WAVE2_TIMING
+    long long t_acc[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     for (;;) {
         if (tid == 0) s_pixel = atomicAdd(p.work_counter, 1u);
@@ -316,6 +329,9 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 
         for (;;) {
             // ======================= 1: owner — closest hit and classification =======================
+#ifdef WAVE2_TIMING
+            long long t_prev = clock64();
+#endif
             uint32_t m = w.meta[tid];
             uint32_t kind = K_NONE;
             if (meta_state(m) == ST_FRESH) {
@@ -414,7 +430,10 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 
             // ======================= 2: bin the slots by kind (one packed scan) =======================
             // per-warp counts travel as two packed words (matte | specular << 16, glossy | terminated << 16); after the
-            // barrier lanes 0..7 of every warp scan the 8 warp totals with three shuffle steps
+            // barrier every warp sums the 8 warp totals, and those of the warps before it, with four independent
+            // REDUX instructions (the item stage was measured to wait on this dependent chain: tools/wave2_timing.py).
+            // Item order: specular | glossy | terminated | matte — the two expensive kinds (matte, glossy) never share a
+            // warp, so the warp that straddles a boundary pays expensive + cheap, not expensive + expensive.
             uint32_t n_matte, n_spec, n_gloss, n_term, pos;
             {
                 const uint32_t bm = __ballot_sync(0xffffffffu, kind == K_MATTE);
@@ -425,43 +444,43 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 if (lane == 0) scr[warp] = make_uint2(__popc(bm) | (__popc(bs) << 16), __popc(bg) | (__popc(bt) << 16));
                 const uint32_t mine = kind == K_MATTE ? bm : (kind == K_SPEC ? bs : (kind == K_GLOSSY ? bg : bt));
                 const uint32_t rank = __popc(mine & lt_mask);
+                TMARK(0);
                 __syncthreads();
-                uint2 inc = lane < WAVE2_S / 32 ? scr[lane] : make_uint2(0u, 0u);
-                const uint2 own = inc;
-#pragma unroll
-                for (uint32_t st = 1; st < WAVE2_S / 32; st <<= 1) {
-                    const uint32_t ux = __shfl_up_sync(0xffffffffu, inc.x, st), uy = __shfl_up_sync(0xffffffffu, inc.y, st);
-                    if (lane >= st) { inc.x += ux; inc.y += uy; }
-                }
-                const uint32_t tx = __shfl_sync(0xffffffffu, inc.x, WAVE2_S / 32 - 1), ty = __shfl_sync(0xffffffffu, inc.y, WAVE2_S / 32 - 1);
-                const uint32_t bx = __shfl_sync(0xffffffffu, inc.x - own.x, warp), by = __shfl_sync(0xffffffffu, inc.y - own.y, warp);
+                TMARK(1);
+                const uint2 v = lane < WAVE2_S / 32 ? scr[lane] : make_uint2(0u, 0u);
+                const uint32_t tx = __reduce_add_sync(0xffffffffu, v.x), ty = __reduce_add_sync(0xffffffffu, v.y);
+                const uint32_t bx = __reduce_add_sync(0xffffffffu, lane < warp ? v.x : 0u);
+                const uint32_t by = __reduce_add_sync(0xffffffffu, lane < warp ? v.y : 0u);
                 n_matte = tx & 0xFFFFu; n_spec = tx >> 16; n_gloss = ty & 0xFFFFu; n_term = ty >> 16;
-                pos = rank + (kind == K_MATTE ? (bx & 0xFFFFu)
-                              : kind == K_SPEC ? n_matte + (bx >> 16)
-                              : kind == K_GLOSSY ? n_matte + n_spec + (by & 0xFFFFu)
-                                                 : n_matte + n_spec + n_gloss + (by >> 16));
+                pos = rank + (kind == K_SPEC ? (bx >> 16)
+                              : kind == K_GLOSSY ? n_spec + (by & 0xFFFFu)
+                              : kind == K_TERM ? n_spec + n_gloss + (by >> 16)
+                                               : n_spec + n_gloss + n_term + (bx & 0xFFFFu));
             }
             const uint32_t n_items = n_matte + n_spec + n_gloss + n_term;
             if (n_items == 0) break;   // every slot idle (uniform)
             if (kind != K_NONE) w.list[pos] = tid;
+            TMARK(2);
             __syncthreads();
+            TMARK(3);
 
             // ======================= 3: one thread per item, in kind order =======================
             if (tid < n_items) {
                 const uint32_t sl = w.list[tid];
                 const uint32_t sm = w.meta[sl];
                 const uint32_t depth = meta_depth(sm), top = meta_top(sm), mi = meta_mat(sm);
-                if (tid < n_matte + n_spec + n_gloss) {
+                const uint32_t a_gloss = n_spec, a_term = n_spec + n_gloss, a_matte = a_term + n_term;   // block starts
+                if (tid < a_term || tid >= a_matte) {
                     const V3 normal = mk3(w.nx[sl], w.ny[sl], w.nz[sl]);
                     const V3 dir = mk3(w.dx[sl], w.dy[sl], w.dz[sl]);
                     const uint32_t i = w.si[sl];
                     V3 wi;
                     double weight, lobe = 1.0;
-                    if (tid < n_matte) {  // materials.rs:19-33
+                    if (tid >= a_matte) {  // materials.rs:19-33
                         if (COUNT) cn[CN_MATTE]++;
                         const double *hp = hs + ((size_t)(depth - 1) * n + i) * 3;
                         matte_sample(normal, mk3(hp[0], hp[1], hp[2]), wi, weight);
-                    } else if (tid < n_matte + n_spec) {  // materials.rs:57-71, brdf.rs:39-45
+                    } else if (tid < a_gloss) {  // materials.rs:57-71, brdf.rs:39-45
                         if (COUNT) cn[CN_SPECULAR]++;
                         specular_sample(normal, dir, wi, weight);
                     } else {  // materials.rs:57-71, brdf.rs:55-78
@@ -504,7 +523,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                         w.acc_b[sl] += Lb;
                     }
                     // terminated slots take the pixel's next sample indices in slot order
-                    const uint32_t i = next + (tid - (n_matte + n_spec + n_gloss));
+                    const uint32_t i = next + (tid - a_term);
                     if (i < n) {
                         const double2 s = ps[i];
                         const double2 l = ds[i];
@@ -528,7 +547,23 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 }
             }
             next += n_term;
+#ifdef WAVE2_TIMING
+            {
+                const long long t_now = clock64();
+                if (lane == 0) {
+                    const uint32_t a1 = n_spec + n_gloss, a2 = a1 + n_term;
+                    const int kk = tid >= n_items ? 3 : (tid >= a2 ? 0 : (tid < a1 ? 1 : 2));
+                    t_acc[7 + 2 * kk] += t_now - t_prev;
+                    t_acc[8 + 2 * kk] += 1;
+                }
+            }
+#endif
+            TMARK(4);
             __syncthreads();
+            TMARK(5);
+#ifdef WAVE2_TIMING
+            if (lane == 0) t_acc[6] += 1;
+#endif
         }
 
         // ---- fixed-shape reduction of the 256 slot sums, then trace.rs:85-86 + color.rs:35-44 ----
@@ -570,6 +605,10 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
         for (int k = 0; k < CN_COUNT; k++)
             if (cn[k]) atomicAdd(p.counters + k, cn[k]);
     }
+#ifdef WAVE2_TIMING
+    if (lane == 0)
+        for (int k = 0; k < 15; k++) atomicAdd(p.counters + k, (unsigned long long)t_acc[k]);
+#endif
 }
 
 }  // namespace
