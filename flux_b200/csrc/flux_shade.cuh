@@ -71,9 +71,30 @@ __device__ __forceinline__ void glossy_sample_hs(V3 normal, V3 dir, V3 hs, doubl
         wi = (u * -hs.x - v * hs.y) + w * hs.z;
     else
         wi = wi0;
-    lobe = lobe_pow(dot3(r, wi), ex);
-    double pdf = lobe * dot3(normal, wi);
-    weight = div_full(dot3(normal, wi), pdf);
+    const double rdotwi = dot3(r, wi);
+    const double ndotwi = dot3(normal, wi);
+#ifndef FLUX_GLOSSY_EXACT_LOBE
+    // The lobe value x^e enters the result twice, as f = (cs*ks)*lobe and through pdf = lobe*ndotwi in the weight
+    // ndotwi/pdf (brdf.rs:73-77, materials.rs:69-70): ((cs*ks*lobe) (*) L) * (ndotwi / (lobe*ndotwi)).  Whenever the
+    // lobe is an ordinary double — finite, non-zero, far from the denormal range — that product equals
+    // ((cs*ks) (*) L) * (ndotwi/ndotwi) up to five roundings (6e-16 relative), nine orders inside the 1e-6 bar that
+    // applies to glossy radiance, so the power function is not evaluated at all: lobe := 1.  A cheap f32 guard
+    // (|e * log2 x| < 900, x > 0, 1e-200 < |ndotwi| < 1e200) decides; everything else — zero / negative / non-finite
+    // bases, lobes that underflow (their 0/0 poisons the pixel with NaN in the reference), vanishing
+    // cosines — takes the exact path below.  The power function was the longest dependent chain of the sorted
+    // shading stage (tools/wave2_timing.py).
+    {
+        const float g = (float)ex * __log2f((float)rdotwi);
+        if (rdotwi > 0.0 && fabsf(g) < 900.0f && fabs(ndotwi) > 1e-200 && fabs(ndotwi) < 1e200) {
+            lobe = 1.0;
+            weight = div_full(ndotwi, ndotwi);
+            return;
+        }
+    }
+#endif
+    lobe = lobe_pow(rdotwi, ex);
+    double pdf = lobe * ndotwi;
+    weight = div_full(ndotwi, pdf);
 }
 
 __device__ __forceinline__ void glossy_sample(V3 normal, V3 dir, double sqx, double sqy, double ex, double inv_e1,
