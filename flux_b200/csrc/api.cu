@@ -618,7 +618,11 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     const bool wave2_ok = wave2_kernel_applicable(p);
     if (ctx->kernel_mode == 4 && !wave2_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: wavefront-2 kernel needs spp >= 256, depth <= 8 and a sphere/plane scene of at most 128 spheres");
-    if (wave2_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 4))
+    // automatic choice on BVH scenes (measured r1): the wavefront kernel wins while the tree is small (config 4, 67
+    // spheres: 2.72 vs 1.90 Gsamples/s), the regeneration kernel on deep trees whose traversal lengths vary a lot
+    // (config 3, 1 M triangles: 567 vs 426 Msamples/s)
+    const bool wave2_auto = wave2_ok && (!p.scene.use_bvh || p.scene.bvh_n_nodes <= 1024);
+    if ((wave2_auto && ctx->kernel_mode == 0) || (wave2_ok && ctx->kernel_mode == 4))
         launch_render_wave2(p, ctx->count, ctx->sm_count, st);
     else if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
         launch_render_wave(p, ctx->count, ctx->sm_count, st);

@@ -33,6 +33,7 @@
 // value is therefore independent of grid size, scheduling and sharding, and equals
 // render_wave.cu's bit for bit (same slot/sample assignment, same summation order).
 #define FLUX_NORM_NOINLINE   // one copy of normalize3_dev per kernel: smaller hot instruction footprint (+1.4 % measured)
+#include "flux_bvh.cuh"
 #include "flux_kernels.cuh"
 #include "flux_shade.cuh"
 
@@ -259,10 +260,13 @@ __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double 
 #define TMARK(k)
 #endif
 
-template <bool COUNT>
+// BVH = true: the owner stage finds the closest hit through the 4-wide BVH over the scene in global memory (meshes,
+// more than 40 bounded shapes; flux_bvh.cuh, traversal stack in local memory) instead of classifying the spheres
+// staged in shared memory; everything else — binning, sorted shading, regeneration — is the same code.
+template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t ns = p.scene.n_spheres, np = p.scene.n_planes, nm = p.scene.n_materials;
+    const uint32_t ns = BVH ? 0u : p.scene.n_spheres, np = BVH ? 0u : p.scene.n_planes, nm = p.scene.n_materials;
     const uint32_t max_depth = p.cam.max_depth;
     const W2Smem w = w2_carve(smem_raw, ns, np, nm, max_depth);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -346,72 +350,91 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     if (COUNT) cn[CN_SEGMENTS]++;
                     const V3 o = mk3(w.ox[tid], w.oy[tid], w.oz[tid]);
                     const V3 d = mk3(w.dx[tid], w.dy[tid], w.dz[tid]);
-                    // ---- spheres: conservative FP32 box classification, exact test where undecided, quadratics ----
-                    // 1/d in f32 from MUFU.RCP (the approximation error is part of E); the exact f64 reciprocals of
-                    // BoundingBox::hit are formed only where a box needs the exact test
-                    CullRay c;
-                    c.iax = rcp_approx((float)d.x); c.iay = rcp_approx((float)d.y); c.iaz = rcp_approx((float)d.z);
-                    const float ofx = (float)o.x, ofy = (float)o.y, ofz = (float)o.z;
-                    c.nox = -(ofx * c.iax); c.noy = -(ofy * c.iay); c.noz = -(ofz * c.iaz);
-                    c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
-                    {
-                        const float ex = c.aax * (p.cull_cmax + fabsf(ofx));
-                        const float ey = c.aay * (p.cull_cmax + fabsf(ofy));
-                        const float ez = c.aaz * (p.cull_cmax + fabsf(ofz));
-                        const float E = fmaxf(fmaxf(ex, ey), ez) * cull_scale;
-                        // outside a sane range (NaN, inf, denormal reciprocals) nothing is decided in FP32
-                        c.e2 = (E > 1e-30f && E < 1e30f) ? 2.0f * E + 4e-9f : __int_as_float(0x7fc00000);
-                    }
-                    const double A = dot3(d, d);
-                    SphereScan sc;
-                    sc.A4 = 4.0 * A;
-                    sc.rA2 = rcp_prepare(2.0 * A);
-                    sc.best_t = 0.0;
-                    sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
-#pragma unroll 1
-                    for (uint32_t base = 0; base < ns; base += 32) sphere_pass<COUNT>(p, w.sph, c, base, ns, o, d, sc, cn);
-                    double best_t = sc.best_t;
-                    uint32_t best_ref = sc.best_ref;
-                    // ---- planes (shapes.rs:137-139) ----
-                    uint32_t best_id = best_ref == 0xFFFFFFFFu ? 0xFFFFFFFFu : w.sph_id[best_ref];
-                    const double *pl = w.pln;
-                    for (uint32_t i = 0; i < np; i++, pl += V_PLN_STRIDE) {
-                        if (COUNT) cn[CN_PLANE_TESTS]++;
-                        const V3 pn = mk3(pl[V_PNX], pl[V_PNY], pl[V_PNZ]);
-                        const double t = div_full(dot3(mk3(pl[V_PPX] - o.x, pl[V_PPY] - o.y, pl[V_PPZ] - o.z), pn), dot3(d, pn));
-                        if (!(t > FLUX_T_MIN)) continue;
-                        if (COUNT) cn[CN_CANDIDATES]++;
-                        const uint32_t id = w.pln_id[i];
-                        if (best_id == 0xFFFFFFFFu || t < best_t || (t == best_t && id < best_id)) {
-                            best_t = t;
-                            best_id = id;
-                            best_ref = 0x80000000u | i;
+                    bool found;
+                    V3 normal = mk3(0.0, 0.0, 0.0), point = mk3(0.0, 0.0, 0.0);
+                    uint32_t mi = 0;
+                    if (BVH) {
+                        uint2 lstack[BVH_STACK];   // local memory: shared memory is taken by the path rows
+                        const RayCtx rc = make_ray(o, d);
+                        const HitRef h = closest_hit_bvh<COUNT>(p.scene, rc, lstack, 1u, cn);
+                        found = h.shape_id != 0xFFFFFFFFu;
+                        if (found) {
+                            const HitRec hrec = build_hit(p.scene, rc, h);
+                            normal = hrec.normal;
+                            point = hrec.point;
+                            mi = hrec.material;
+                            if (COUNT) cn[h.kind == KIND_SPHERE ? CN_HIT_SPHERE : (h.kind == KIND_PLANE ? CN_HIT_PLANE : CN_HIT_TRI)]++;
+                        }
+                    } else {
+                        // ---- spheres: conservative FP32 box classification, exact test where undecided, quadratics ----
+                        // 1/d in f32 from MUFU.RCP (the approximation error is part of E); the exact f64 reciprocals of
+                        // BoundingBox::hit are formed only where a box needs the exact test
+                        CullRay c;
+                        c.iax = rcp_approx((float)d.x); c.iay = rcp_approx((float)d.y); c.iaz = rcp_approx((float)d.z);
+                        const float ofx = (float)o.x, ofy = (float)o.y, ofz = (float)o.z;
+                        c.nox = -(ofx * c.iax); c.noy = -(ofy * c.iay); c.noz = -(ofz * c.iaz);
+                        c.aax = fabsf(c.iax); c.aay = fabsf(c.iay); c.aaz = fabsf(c.iaz);
+                        {
+                            const float ex = c.aax * (p.cull_cmax + fabsf(ofx));
+                            const float ey = c.aay * (p.cull_cmax + fabsf(ofy));
+                            const float ez = c.aaz * (p.cull_cmax + fabsf(ofz));
+                            const float E = fmaxf(fmaxf(ex, ey), ez) * cull_scale;
+                            // outside a sane range (NaN, inf, denormal reciprocals) nothing is decided in FP32
+                            c.e2 = (E > 1e-30f && E < 1e30f) ? 2.0f * E + 4e-9f : __int_as_float(0x7fc00000);
+                        }
+                        const double A = dot3(d, d);
+                        SphereScan sc;
+                        sc.A4 = 4.0 * A;
+                        sc.rA2 = rcp_prepare(2.0 * A);
+                        sc.best_t = 0.0;
+                        sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
+    #pragma unroll 1
+                        for (uint32_t base = 0; base < ns; base += 32) sphere_pass<COUNT>(p, w.sph, c, base, ns, o, d, sc, cn);
+                        double best_t = sc.best_t;
+                        uint32_t best_ref = sc.best_ref;
+                        // ---- planes (shapes.rs:137-139) ----
+                        uint32_t best_id = best_ref == 0xFFFFFFFFu ? 0xFFFFFFFFu : w.sph_id[best_ref];
+                        const double *pl = w.pln;
+                        for (uint32_t i = 0; i < np; i++, pl += V_PLN_STRIDE) {
+                            if (COUNT) cn[CN_PLANE_TESTS]++;
+                            const V3 pn = mk3(pl[V_PNX], pl[V_PNY], pl[V_PNZ]);
+                            const double t = div_full(dot3(mk3(pl[V_PPX] - o.x, pl[V_PPY] - o.y, pl[V_PPZ] - o.z), pn), dot3(d, pn));
+                            if (!(t > FLUX_T_MIN)) continue;
+                            if (COUNT) cn[CN_CANDIDATES]++;
+                            const uint32_t id = w.pln_id[i];
+                            if (best_id == 0xFFFFFFFFu || t < best_t || (t == best_t && id < best_id)) {
+                                best_t = t;
+                                best_id = id;
+                                best_ref = 0x80000000u | i;
+                            }
+                        }
+                        found = best_id != 0xFFFFFFFFu;
+                        if (found) {
+                            // hit record of the closest hit only (shapes.rs:140-147,191-198)
+                            point = o + best_t * d;
+                            if (best_ref & 0x80000000u) {
+                                const uint32_t k = best_ref & 0x7FFFFFFFu;
+                                const double *q = w.pln + (size_t)k * V_PLN_STRIDE;
+                                normal = mk3(q[V_PNX], q[V_PNY], q[V_PNZ]);
+                                mi = w.pln_mat[k];
+                                if (COUNT) cn[CN_HIT_PLANE]++;
+                            } else {
+                                const double *s = w.sph + (size_t)best_ref * V_SPH_STRIDE;
+                                const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
+                                const V3 nn = (temp + best_t * d) * s[V_INV];
+                                RcpD rr;
+                                rr.b = s[V_RB]; rr.y = s[V_RY]; rr.ok = s[V_OK] != 0.0;
+                                normal = V3{div_by(nn.x, rr), div_by(nn.y, rr), div_by(nn.z, rr)};
+                                mi = w.sph_mat[best_ref];
+                                if (COUNT) cn[CN_HIT_SPHERE]++;
+                            }
                         }
                     }
-                    if (best_id == 0xFFFFFFFFu) {  // scene.rs:168
+                    if (!found) {  // scene.rs:168
                         if (COUNT) cn[CN_MISS]++;
                         kind = K_TERM;
                         w.meta[tid] = meta_pack(depth, top, 0, ST_ALIVE, T_BACKGROUND);
                     } else {
-                        // hit record of the closest hit only (shapes.rs:140-147,191-198)
-                        V3 normal;
-                        uint32_t mi;
-                        if (best_ref & 0x80000000u) {
-                            const uint32_t k = best_ref & 0x7FFFFFFFu;
-                            const double *q = w.pln + (size_t)k * V_PLN_STRIDE;
-                            normal = mk3(q[V_PNX], q[V_PNY], q[V_PNZ]);
-                            mi = w.pln_mat[k];
-                            if (COUNT) cn[CN_HIT_PLANE]++;
-                        } else {
-                            const double *s = w.sph + (size_t)best_ref * V_SPH_STRIDE;
-                            const V3 temp = mk3(o.x - s[V_CX], o.y - s[V_CY], o.z - s[V_CZ]);
-                            const V3 nn = (temp + best_t * d) * s[V_INV];
-                            RcpD rr;
-                            rr.b = s[V_RB]; rr.y = s[V_RY]; rr.ok = s[V_OK] != 0.0;
-                            normal = V3{div_by(nn.x, rr), div_by(nn.y, rr), div_by(nn.z, rr)};
-                            mi = w.sph_mat[best_ref];
-                            if (COUNT) cn[CN_HIT_SPHERE]++;
-                        }
                         const uint32_t mk = w.mat[mi].kind;
                         if (mk == FLUX_MAT_EMISSIVE) {  // materials.rs:42-49
                             if (COUNT) cn[CN_EMISSIVE]++;
@@ -419,7 +442,6 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                             w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, dot3(normal * -1.0, d) > 0.0 ? T_EMIT : T_BLACK);
                         } else {
                             kind = mk == FLUX_MAT_MATTE ? K_MATTE : (mk == FLUX_MAT_REFLECTIVE ? K_SPEC : K_GLOSSY);
-                            const V3 point = o + best_t * d;
                             w.nx[tid] = normal.x; w.ny[tid] = normal.y; w.nz[tid] = normal.z;
                             w.ox[tid] = point.x; w.oy[tid] = point.y; w.oz[tid] = point.z;  // child ray origin
                             w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, 0);
@@ -613,24 +635,34 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 
 }  // namespace
 
-// Applies when a CTA can own a pixel (spp >= 256; the per-pixel drain tail is ~2 % at 16384 spp), the scene has only
-// spheres and planes, at most FLUX_CULL_MAX = 128 spheres / 255 materials, and depth <= 8.
+// Applies when a CTA can own a pixel (spp >= 256; the per-pixel drain tail is ~2 % at 16384 spp), depth <= 8, at most
+// 255 materials, and the scene either goes through the BVH or has only spheres (at most FLUX_CULL_MAX = 128) and planes.
+static size_t w2_smem_for(const RenderParams &p) {
+    return p.scene.use_bvh ? w2_smem_bytes(0, 0, p.scene.n_materials, p.cam.max_depth)
+                           : w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth);
+}
+
 bool wave2_kernel_applicable(const RenderParams &p) {
-    return p.ss.n >= WAVE2_MIN_SPP && p.scene.n_tris == 0 && !p.scene.use_bvh && p.scene.n_spheres <= FLUX_CULL_MAX &&
-           p.scene.n_materials <= 255 && p.cam.max_depth >= 1 && p.cam.max_depth <= WAVE2_MAX_DEPTH &&
-           w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth) <= (size_t)(226 * 1024) / 3 - 1024;   // at least 3 CTAs per SM
+    if (p.ss.n < WAVE2_MIN_SPP || p.scene.n_materials > 255 || p.cam.max_depth < 1 || p.cam.max_depth > WAVE2_MAX_DEPTH) return false;
+    if (!p.scene.use_bvh && (p.scene.n_tris != 0 || p.scene.n_spheres > FLUX_CULL_MAX)) return false;
+    return w2_smem_for(p) <= (size_t)(226 * 1024) / 3 - 1024;   // at least 3 CTAs per SM
 }
 
 void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
-    const size_t smem = w2_smem_bytes(p.scene.n_spheres, p.scene.n_planes, p.scene.n_materials, p.cam.max_depth);
+    const size_t smem = w2_smem_for(p);
     const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;
     const uint64_t cap = (uint64_t)sm_count * WAVE2_MIN_BLOCKS;
     const int blocks = (int)(npix < cap ? (npix ? npix : 1) : cap);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, WAVE2_S, smem, stream>>>(p);
+    };
+    const bool bvh = p.scene.use_bvh != 0;
     if (count) {
-        cudaFuncSetAttribute(render_wave2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_wave2_kernel<true><<<blocks, WAVE2_S, smem, stream>>>(p);
+        if (bvh) go(render_wave2_kernel<true, true>);
+        else go(render_wave2_kernel<true, false>);
     } else {
-        cudaFuncSetAttribute(render_wave2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        render_wave2_kernel<false><<<blocks, WAVE2_S, smem, stream>>>(p);
+        if (bvh) go(render_wave2_kernel<false, true>);
+        else go(render_wave2_kernel<false, false>);
     }
 }

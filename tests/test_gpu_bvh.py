@@ -197,3 +197,50 @@ def test_mesh_scene_regeneration_kernel_with_bvh(gpu_ctx):
     gpu_ctx.set_kernel_mode(0)
     auto = gpu_ctx.render_rows(0, 23, 32)
     assert np.array_equal(auto.view(np.uint64), imgs[2].view(np.uint64))   # auto mode = regeneration kernel here
+
+
+def test_mesh_scene_wavefront_kernel_with_bvh(gpu_ctx):
+    """spp >= 256 on a BVH scene selects the wavefront kernel whose owner stage traverses the BVH: must agree with
+    the oracle's linear scan (matte mesh, emissive spheres: 1e-12) and reproduce the regeneration kernel's counters."""
+    sd = synth.mesh_scene(40, 24, seed=3, width=24, height=16)
+    cfg = JobConfiguration(16, 5, 50)
+    ss = Hp.oracle_samples(10, cfg, 24, 16)
+    flat = sd.flatten()
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    imgs, cns = {}, {}
+    try:
+        for mode in (2, 4):
+            gpu_ctx.set_kernel_mode(mode)
+            gpu_ctx.enable_counters(True)
+            gpu_ctx.reset_counters()
+            imgs[mode] = gpu_ctx.render_rows(0, 15, 24)
+            cns[mode] = gpu_ctx.counters()
+            gpu_ctx.enable_counters(False)
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.enable_counters(False)
+    ref = O.render_rows(flat, cfg, ss, 0, 15)
+    assert Hp.rel_err(imgs[4], ref) <= 1e-12
+    assert Hp.rel_err(imgs[2], ref) <= 1e-12
+    assert cns[2] == cns[4] and cns[4]["hit_tri"] > 0 and cns[4]["nodes_visited"] > 0
+    auto = gpu_ctx.render_rows(0, 15, 24)
+    assert np.array_equal(auto.view(np.uint64), imgs[4].view(np.uint64))   # auto mode = wavefront kernel here
+
+
+def test_glossy_67_sphere_scene_wavefront_bvh_matches_oracle(gpu_ctx):
+    """Config 4 shape through the automatic choice (BVH + wavefront kernel): all four shading kinds, 67 spheres."""
+    sd = synth.glossy_scene(24, 14, seed=4)
+    cfg = JobConfiguration(16, 5, 50)
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(24, cfg, 24, 14)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    gpu_ctx.enable_counters(True)
+    gpu_ctx.reset_counters()
+    img = gpu_ctx.render_rows(0, 13, 24)
+    cn = gpu_ctx.counters()
+    gpu_ctx.enable_counters(False)
+    ref, cn_o = O.render_rows(flat, cfg, ss, 0, 13, counters=True)
+    assert Hp.rel_err(img, ref) <= 1e-6
+    assert cn["nodes_visited"] > 0
+    for k in ("samples", "segments", "hit_sphere", "hit_plane", "emissive", "matte", "specular", "glossy", "miss", "depth_cut"):
+        assert abs(cn[k] - cn_o[k]) <= max(2, 1e-6 * cn_o[k]), (k, cn[k], cn_o[k])

@@ -75,8 +75,11 @@ def c5(ctx, n_total=100_000_000, chunk=10_000_000):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"c1", "c3", "c4", "c5"}
+    args = [a for a in sys.argv[1:] if not a.startswith("--mode=")]
+    mode = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--mode=")), 0)
+    which = set(args) or {"c1", "c3", "c4", "c5"}
     ctx = GpuContext(0)
+    ctx.set_kernel_mode(mode)   # 0 = auto; A/B of render kernels on the same config
     if "c1" in which:
         sd = SceneData.from_yaml(os.path.join(ROOT, "scenes", "demo1.yml")).with_size(512, 512)
         render_config(ctx, "c1 demo1 512x512 @16spp", sd, 4, reps=5)
