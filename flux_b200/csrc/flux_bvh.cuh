@@ -117,47 +117,67 @@ __device__ __forceinline__ bool tri_t_rec(const RayCtx &r, const TriRec *__restr
     return true;
 }
 
-// Scene::hit through the BVH.  `stack` points at this thread's column of a [BVH_STACK][blockDim.x] uint2
-// array in shared memory (entry e of thread t at stack[e * stride]).
+// Scene::hit through the BVH as an explicit traversal state, so that a kernel can interleave traversals with
+// fetching new rays (trace_rays_kernel) as well as run one to completion (closest_hit_bvh).  `stack` points at this
+// thread's column of a [BVH_STACK][stride] uint2 array (entry e at stack[e * stride]); shared or local memory.
+//
+// "while-while" order: descend() keeps a lane on inner nodes until it holds a leaf (or is done) before leaf() runs the
+// f64 primitive tests, so the two very different code paths each execute with most of the warp (ncu on an if/else
+// loop: 6.9 of 32 lanes per instruction on incoherent rays, profiles/r1s_bvh_kernels_full.txt).
 template <bool COUNT>
-__device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayCtx &r, uint2 *stack, uint32_t stride,
-                                                  unsigned long long *cn) {
+struct BvhTraversal {
+    RayCtx r;
     HitRef best;
-    best.t = 0.0;
-    best.shape_id = 0xFFFFFFFFu;
-    best.kind = 0;
-    best.index = 0;
-    const double inf = __longlong_as_double(0x7FF0000000000000ll);
-    // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k|
-    const double tscale = sc.bvh_extent * fmin(fabs(r.ia), fmin(fabs(r.ib), fabs(r.ic)));
-    double t_prune = inf;
-#define BVH_CONSIDER(T, ID, KIND, INDEX)                                               \
-    do {                                                                               \
-        if (COUNT) cn[CN_CANDIDATES]++;                                                \
-        consider(best, (T), (ID), (KIND), (INDEX));                                    \
-        t_prune = best.t + BVH_PRUNE_REL * (fabs(best.t) + tscale);                    \
-    } while (0)
-
-    // ---- unbounded / oversized shapes: linear, first (they tighten t_prune early) ----
-    for (uint32_t i = 0; i < sc.n_planes; i++) {
-        double t;
-        if (COUNT) cn[CN_PLANE_TESTS]++;
-        if (plane_t(r, sc.pln, sc.n_planes, i, t)) BVH_CONSIDER(t, __ldg(sc.pln_meta + i), KIND_PLANE, i);
-    }
-    for (uint32_t k = 0; k < sc.bvh_n_linear; k++) {
-        const uint32_t i = __ldg(sc.bvh_linear + k);
-        double t;
-        if (sphere_t<COUNT>(r, sc.sph, sc.n_spheres, i, t, cn)) BVH_CONSIDER(t, __ldg(sc.sph_meta + i), KIND_SPHERE, i);
-    }
-    if (sc.bvh_n_nodes == 0) return best;
-
-    const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
-    const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
-    const TriRec *__restrict__ trec = reinterpret_cast<const TriRec *>(sc.bvh_tri);
-    // ---- f32 ray constants: near = fma(c_near, ia, nlo) <= exact entry, far = fma(c_far, ia, nhi) >= exact exit ----
+    double t_prune, tscale, t_prune_seen;
+    float t_prune32;
     float ia32[3], nlo[3], nhi[3];
     bool pos[3];
-    {
+    uint32_t sp, cur;   // cur: inner node index | leaf reference | BVH_EMPTY (done; carries the leaf bit)
+
+    __device__ __forceinline__ bool done() const { return cur == BVH_EMPTY; }
+
+    __device__ __forceinline__ void candidate(double t, uint32_t id, uint32_t kind, uint32_t index, unsigned long long *cn) {
+        if (COUNT) cn[CN_CANDIDATES]++;
+        consider(best, t, id, kind, index);
+        t_prune = best.t + BVH_PRUNE_REL * (fabs(best.t) + tscale);
+    }
+
+    // pop the nearest stacked subtree that can still hold a closer hit
+    __device__ __forceinline__ void pop(const uint2 *stack, uint32_t stride) {
+        cur = BVH_EMPTY;
+        while (sp) {
+            sp--;
+            const uint2 e = stack[(size_t)sp * stride];
+            if ((double)__uint_as_float(e.y) > t_prune) continue;   // became prunable since it was pushed
+            cur = e.x;
+            break;
+        }
+    }
+
+    // unbounded / oversized shapes first (they tighten t_prune early), then the f32 ray constants
+    __device__ __forceinline__ void begin(const DevScene &sc, const RayCtx &ray, unsigned long long *cn) {
+        r = ray;
+        best.t = 0.0;
+        best.shape_id = 0xFFFFFFFFu;
+        best.kind = 0;
+        best.index = 0;
+        const double inf = __longlong_as_double(0x7FF0000000000000ll);
+        // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k|
+        tscale = sc.bvh_extent * fmin(fabs(r.ia), fmin(fabs(r.ib), fabs(r.ic)));
+        t_prune = inf;
+        for (uint32_t i = 0; i < sc.n_planes; i++) {
+            double t;
+            if (COUNT) cn[CN_PLANE_TESTS]++;
+            if (plane_t(r, sc.pln, sc.n_planes, i, t)) candidate(t, __ldg(sc.pln_meta + i), KIND_PLANE, i, cn);
+        }
+        for (uint32_t k = 0; k < sc.bvh_n_linear; k++) {
+            const uint32_t i = __ldg(sc.bvh_linear + k);
+            double t;
+            if (sphere_t<COUNT>(r, sc.sph, sc.n_spheres, i, t, cn)) candidate(t, __ldg(sc.sph_meta + i), KIND_SPHERE, i, cn);
+        }
+        sp = 0;
+        cur = sc.bvh_n_nodes ? 0u : BVH_EMPTY;   // root
+        // f32 ray constants: near = fma(c_near, ia, nlo) <= exact entry, far = fma(c_far, ia, nhi) >= exact exit
         const double dd[3] = {r.d.x, r.d.y, r.d.z}, oo[3] = {r.o.x, r.o.y, r.o.z};
         const float ext = __double2float_ru(sc.bvh_extent);
 #pragma unroll
@@ -175,27 +195,13 @@ __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayC
             nlo[k] = sane ? noa - E : -CUDART_INF_F;   // an axis that cannot be bounded constrains nothing
             nhi[k] = sane ? noa + E : CUDART_INF_F;
         }
+        t_prune32 = CUDART_INF_F;   // >= t_prune, refreshed lazily
+        t_prune_seen = inf;
     }
-    float t_prune32 = CUDART_INF_F;   // >= t_prune, refreshed lazily
-    double t_prune_seen = inf;
-    uint32_t sp = 0;
-    uint32_t cur = 0;  // root
-    // pop the nearest stacked subtree that can still hold a closer hit; BVH_EMPTY (which carries the leaf bit) when none
-#define BVH_POP()                                                                                        \
-    {                                                                                                    \
-        cur = BVH_EMPTY;                                                                                 \
-        while (sp) {                                                                                     \
-            sp--;                                                                                        \
-            const uint2 e = stack[(size_t)sp * stride];                                                  \
-            if ((double)__uint_as_float(e.y) > t_prune) continue; /* became prunable since it was pushed */ \
-            cur = e.x;                                                                                   \
-            break;                                                                                       \
-        }                                                                                                \
-    }
-    // "while-while" traversal: every lane keeps descending inner nodes until it holds a leaf (or is done) before any
-    // lane runs the f64 primitive tests, so the two very different code paths each execute with most of the warp
-    // (ncu on the if/else form: 6.9 of 32 lanes per instruction on incoherent rays, profiles/r1s_bvh_kernels_full.txt)
-    for (;;) {
+
+    // inner nodes until this lane holds a leaf or has nothing left
+    __device__ __forceinline__ void descend(const DevScene &sc, uint2 *stack, uint32_t stride, unsigned long long *cn) {
+        const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
         while (!(cur & BVH_LEAF)) {
             if (COUNT) cn[CN_NODES]++;
             if (t_prune != t_prune_seen) {
@@ -238,29 +244,43 @@ __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayC
                     sp++;
                 }
             if (ref[0] != BVH_EMPTY) cur = ref[0];
-            else BVH_POP()
+            else pop(stack, stride);
         }
-        if (cur == BVH_EMPTY) return best;
-        {
-            const uint32_t off = (cur & 0x7FFFFFFFu) >> 3, cnt = (cur & 7u) + 1u;
-            for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t pr = __ldg(sc.bvh_prims + off + k);
-                const uint32_t idx = pr & 0x3FFFFFFFu;
-                double t;
-                if ((pr >> 30) == KIND_SPHERE) {
-                    const SphRec *s = srec + idx;
-                    if (sphere_t_rec<COUNT>(r, s, t, cn)) BVH_CONSIDER(t, __ldg(&s->shape_id), KIND_SPHERE, idx);
-                } else {
-                    const TriRec *q = trec + idx;
-                    if (COUNT) cn[CN_TRI_TESTS]++;
-                    if (tri_t_rec(r, q, t)) BVH_CONSIDER(t, __ldg(&q->shape_id), KIND_TRI, idx);
-                }
+    }
+
+    // the f64 primitive tests of the leaf this lane holds (the very functions of the linear scan), then the next subtree
+    __device__ __forceinline__ void leaf(const DevScene &sc, const uint2 *stack, uint32_t stride, unsigned long long *cn) {
+        const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
+        const TriRec *__restrict__ trec = reinterpret_cast<const TriRec *>(sc.bvh_tri);
+        const uint32_t off = (cur & 0x7FFFFFFFu) >> 3, cnt = (cur & 7u) + 1u;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t pr = __ldg(sc.bvh_prims + off + k);
+            const uint32_t idx = pr & 0x3FFFFFFFu;
+            double t;
+            if ((pr >> 30) == KIND_SPHERE) {
+                const SphRec *s = srec + idx;
+                if (sphere_t_rec<COUNT>(r, s, t, cn)) candidate(t, __ldg(&s->shape_id), KIND_SPHERE, idx, cn);
+            } else {
+                const TriRec *q = trec + idx;
+                if (COUNT) cn[CN_TRI_TESTS]++;
+                if (tri_t_rec(r, q, t)) candidate(t, __ldg(&q->shape_id), KIND_TRI, idx, cn);
             }
         }
-        BVH_POP()
+        pop(stack, stride);
     }
-#undef BVH_POP
-#undef BVH_CONSIDER
+};
+
+template <bool COUNT>
+__device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayCtx &r, uint2 *stack, uint32_t stride,
+                                                  unsigned long long *cn) {
+    BvhTraversal<COUNT> T;
+    T.begin(sc, r, cn);
+    while (!T.done()) {
+        T.descend(sc, stack, stride, cn);
+        if (T.done()) break;
+        T.leaf(sc, stack, stride, cn);
+    }
+    return T.best;
 }
 #endif  // __CUDACC__
 
