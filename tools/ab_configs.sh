@@ -1,4 +1,4 @@
-for so in flux_b200/lib/variants/lib_*.so; do echo $so; FLUXB200_LIB=$PWD/$so timeout 600 python tools/bench_configs.py c5 c3 2>&1 | grep -v linear | python -c "
+for so in flux_b200/lib/variants/lib_*.so; do echo $so; FLUXB200_LIB=$PWD/$so timeout 600 python tools/bench_configs.py ${AB_CONFIGS:-c3} 2>&1 | grep -v linear | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
