@@ -3,10 +3,12 @@
 // SceneData model with serde's "every field required, unknown keys ignored" behaviour, flattening for the
 // C-ABI, and the GpuWorker that drives libfluxb200.so.
 #include "fluxhost.hpp"
+#include "node.hpp"
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -20,20 +22,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // YAML subset
 // ------------------------------------------------------------------------------------------------
-struct Node {
-    enum Kind { Null, Scalar, Seq, Map } kind = Null;
-    std::string scalar;
-    bool quoted = false;
-    std::vector<Node> seq;
-    std::vector<std::pair<std::string, Node>> map;
-
-    const Node *find(const std::string &key) const {
-        if (kind != Map) return nullptr;
-        for (auto &kv : map)
-            if (kv.first == key) return &kv.second;
-        return nullptr;
-    }
-};
+using detail::Node;
 
 struct Line {
     int indent;
@@ -304,7 +293,10 @@ const Node &req(const Node &m, const char *key, const char *what) {
 }
 
 double as_f64(const Node &n, const std::string &what) {
-    if (n.kind == Node::Scalar && !n.quoted) {
+    if (n.kind == Node::Scalar && n.bin == Node::F64) return n.f;
+    if (n.kind == Node::Scalar && n.bin == Node::U64) return (double)n.u;   // serde's f64 visitor takes integers
+    if (n.kind == Node::Scalar && n.bin == Node::I64) return (double)(int64_t)n.u;
+    if (n.kind == Node::Scalar && n.bin == Node::Text && !n.quoted) {
         const std::string &t = n.scalar;
         if (t == ".inf" || t == "+.inf" || t == ".Inf") return INFINITY;
         if (t == "-.inf" || t == "-.Inf") return -INFINITY;
@@ -319,7 +311,8 @@ double as_f64(const Node &n, const std::string &what) {
 }
 
 uint32_t as_usize(const Node &n, const std::string &what) {
-    if (n.kind == Node::Scalar && !n.quoted && !n.scalar.empty() && n.scalar.find_first_not_of("0123456789") == std::string::npos) {
+    if (n.kind == Node::Scalar && n.bin == Node::U64 && n.u <= 0xFFFFFFFFull) return (uint32_t)n.u;
+    if (n.kind == Node::Scalar && n.bin == Node::Text && !n.quoted && !n.scalar.empty() && n.scalar.find_first_not_of("0123456789") == std::string::npos) {
         const unsigned long long v = std::strtoull(n.scalar.c_str(), nullptr, 10);
         if (v <= 0xFFFFFFFFull) return (uint32_t)v;
     }
@@ -327,7 +320,8 @@ uint32_t as_usize(const Node &n, const std::string &what) {
 }
 
 bool as_bool(const Node &n, const std::string &what) {
-    if (n.kind == Node::Scalar && !n.quoted) {
+    if (n.kind == Node::Scalar && n.bin == Node::Bool) return n.u != 0;
+    if (n.kind == Node::Scalar && n.bin == Node::Text && !n.quoted) {
         if (n.scalar == "true") return true;
         if (n.scalar == "false") return false;
     }
@@ -404,7 +398,7 @@ ShapeData shape_from_yaml(const Node &n) {
     throw Error("unknown variant `" + tag + "`, expected `Sphere` or `Plane`");
 }
 
-SceneData scene_from_node(const Node &d) {
+SceneData scene_from_tree(const Node &d) {
     if (d.kind != Node::Map) throw Error("SceneData: expected a map");
     const char *what = "SceneData";
     const Node &os = req(d, "output_settings", what), &cs = req(d, "camera_settings", what), &cd = req(d, "camera_data", what);
@@ -473,7 +467,11 @@ std::vector<RectangleData> box_rectangles(const BoxData &b) {
 // ------------------------------------------------------------------------------------------------
 // SceneData
 // ------------------------------------------------------------------------------------------------
-SceneData SceneData::from_yaml_string(const std::string &text) { return scene_from_node(Parser(text).parse()); }
+SceneData SceneData::from_yaml_string(const std::string &text) { return scene_from_tree(Parser(text).parse()); }
+
+namespace detail {
+SceneData scene_from_node(const Node &d) { return scene_from_tree(d); }
+}  // namespace detail
 
 SceneData SceneData::from_yaml_file(const std::string &path) {
     std::ifstream f(path);
@@ -584,6 +582,53 @@ std::unique_ptr<FlatScene> SceneData::flatten() const {
     return fs;
 }
 
+// Flattened scene as text, doubles in hex-float so the comparison with the Python loader is exact.
+void dump_flat_text(const std::string &path, FlatScene &f) {
+    FILE *o = std::fopen(path.c_str(), "w");
+    if (!o) throw Error("cannot write `" + path + "`");
+    const flux_scene_flat &s = *f.ptr();
+    auto dv = [&](const char *name, const double *p, size_t n) {
+        std::fprintf(o, "%s %zu", name, n);
+        for (size_t i = 0; i < n; i++) std::fprintf(o, " %a", p[i]);
+        std::fprintf(o, "\n");
+    };
+    auto uv = [&](const char *name, const uint32_t *p, size_t n) {
+        std::fprintf(o, "%s %zu", name, n);
+        for (size_t i = 0; i < n; i++) std::fprintf(o, " %u", p[i]);
+        std::fprintf(o, "\n");
+    };
+    std::fprintf(o, "image %u %u\n", s.image_width, s.image_height);
+    const double scal[] = {s.pixel_size, s.zoom_factor, s.view_plane_distance, s.focal_distance, s.lens_radius};
+    dv("scalars", scal, 5);
+    dv("background", s.background, 3);
+    dv("eye", s.eye, 3);
+    dv("look_at", s.look_at, 3);
+    dv("up", s.up, 3);
+    std::fprintf(o, "materials %u\n", s.n_materials);
+    for (uint32_t i = 0; i < s.n_materials; i++) {
+        const flux_material &m = s.materials[i];
+        std::fprintf(o, "material %u %a %a %a %a %a\n", m.kind, m.color[0], m.color[1], m.color[2], m.k, m.exp);
+    }
+    dv("sphere_center", s.sphere_center, 3 * (size_t)s.n_spheres);
+    dv("sphere_radius", s.sphere_radius, s.n_spheres);
+    std::fprintf(o, "sphere_invert %u", s.n_spheres);
+    for (uint32_t i = 0; i < s.n_spheres; i++) std::fprintf(o, " %u", (unsigned)s.sphere_invert[i]);
+    std::fprintf(o, "\n");
+    uv("sphere_shape_id", s.sphere_shape_id, s.n_spheres);
+    uv("sphere_material", s.sphere_material, s.n_spheres);
+    dv("plane_point", s.plane_point, 3 * (size_t)s.n_planes);
+    dv("plane_normal", s.plane_normal, 3 * (size_t)s.n_planes);
+    uv("plane_shape_id", s.plane_shape_id, s.n_planes);
+    uv("plane_material", s.plane_material, s.n_planes);
+    dv("tri_v0", s.tri_v0, 3 * (size_t)s.n_triangles);
+    dv("tri_v1", s.tri_v1, 3 * (size_t)s.n_triangles);
+    dv("tri_v2", s.tri_v2, 3 * (size_t)s.n_triangles);
+    uv("tri_shape_id", s.tri_shape_id, s.n_triangles);
+    uv("tri_material", s.tri_material, s.n_triangles);
+    std::fclose(o);
+}
+
+
 std::vector<WorkUnit> work_units(uint32_t image_height, uint32_t rows_per_work_unit, uint64_t job_id) {
     if (rows_per_work_unit == 0) throw Error("rows_per_work_unit must be >= 1");
     std::vector<WorkUnit> u;
@@ -678,6 +723,64 @@ std::vector<WorkUnitResult> GpuWorker::run_job(const SceneData &sd, const JobCon
         out.push_back(camera.render(scene, u));
     }
     return out;
+}
+
+void GpuWorker::begin_job(const SceneData &sd, const JobConfiguration &cfg) {
+    auto job = std::make_unique<ActiveJob>();
+    job->scene = Scene::from_data(sd, cfg);
+    job->width = sd.output_settings.image_width;
+    job->height = sd.output_settings.image_height;
+    const uint32_t world = (uint32_t)devices_.size();
+    std::vector<std::string> errors(world);
+    std::vector<std::unique_ptr<Camera>> cams(world);
+    auto setup = [&](uint32_t rank) {
+        try {
+            cams[rank] = std::make_unique<Camera>(Camera::create(*contexts_[rank], job->scene, cfg, job->width, seed_));
+        } catch (const std::exception &e) {
+            errors[rank] = e.what();
+        }
+    };
+    if (world == 1) {
+        setup(0);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t r = 0; r < world; r++) th.emplace_back(setup, r);
+        for (auto &t : th) t.join();
+    }
+    for (const std::string &e : errors)
+        if (!e.empty()) throw Error(e);
+    for (auto &c : cams) job->cameras.push_back(*c);
+    job_ = std::move(job);
+}
+
+WorkUnitResult GpuWorker::render_unit(const WorkUnit &unit) {
+    if (!job_) throw Error("GpuWorker::render_unit: no job");
+    if (unit.row_end < unit.row_start || unit.row_end >= job_->height) throw Error("GpuWorker::render_unit: rows outside the image");
+    const uint32_t world = (uint32_t)devices_.size();
+    if (world == 1) return job_->cameras[0].render(job_->scene, unit);
+    const size_t row_elems = (size_t)job_->width * 3;
+    WorkUnitResult res{unit, std::vector<double>((size_t)(unit.row_end - unit.row_start + 1) * row_elems)};
+    std::vector<std::string> errors(world);
+    auto shard = [&](uint32_t rank) {
+        try {
+            std::vector<uint32_t> rows;   // same ownership rule as flux_shard_rows, restricted to the unit
+            for (uint32_t r = unit.row_start; r <= unit.row_end; r++)
+                if ((r / tile_rows_) % world == rank) rows.push_back(r);
+            if (rows.empty()) return;
+            const std::vector<double> px = job_->cameras[rank].render_row_list(rows);
+            for (size_t k = 0; k < rows.size(); k++)
+                std::copy(px.begin() + k * row_elems, px.begin() + (k + 1) * row_elems,
+                          res.rows.begin() + (size_t)(rows[k] - unit.row_start) * row_elems);
+        } catch (const std::exception &e) {
+            errors[rank] = e.what();
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t r = 0; r < world; r++) th.emplace_back(shard, r);
+    for (auto &t : th) t.join();
+    for (const std::string &e : errors)
+        if (!e.empty()) throw Error(e);
+    return res;
 }
 
 Image GpuWorker::render_job(const SceneData &sd, const JobConfiguration &cfg, double *render_seconds) {

@@ -61,7 +61,9 @@ struct JobConfiguration {          // job.rs:49-53; defaults flux/src/main.rs:20
     uint32_t rows_per_work_unit = 50;
 };
 
-struct WorkUnit { uint32_t row_start, row_end; uint64_t job_id; };   // job.rs:40-44, row_end inclusive
+// job.rs:40-44, row_end inclusive.  JobID is (allocator id, serial) in the reference (job.rs:10): job_id is the
+// serial, job_allocator_id the allocator's random id; both travel back unchanged in the WorkUnitResult.
+struct WorkUnit { uint32_t row_start, row_end; uint64_t job_id; uint64_t job_allocator_id = 0; };
 struct WorkUnitResult {                                             // manager.rs:25-28
     WorkUnit work_unit;
     std::vector<double> rows;   // [row_end-row_start+1][W][3], linear RGB, averaged and max_to_one-clamped
@@ -95,6 +97,9 @@ struct SceneData {   // scene.rs:42-49
     // plain data -> per-kind arrays with one shared shape-id space (include/fluxb200.h flux_scene_flat)
     std::unique_ptr<FlatScene> flatten() const;
 };
+
+// The flattened scene as text, doubles in hex-float: what the tests compare with the Python mirror's flattening.
+void dump_flat_text(const std::string &path, FlatScene &f);
 
 // Job::work_units (job.rs:66-88) without its dropped-trailing-row quirk: covers every row.
 std::vector<WorkUnit> work_units(uint32_t image_height, uint32_t rows_per_work_unit, uint64_t job_id = 0);
@@ -162,8 +167,21 @@ class GpuWorker {
     // JobHandle::cancel / CancellableIterator (manager.rs:66-69,365-393): once set, no further unit is issued; the
     // unit in flight finishes; the rows rendered so far are returned (missing rows stay black in an Image).
     std::vector<WorkUnitResult> run_job(const SceneData &sd, const JobConfiguration &cfg, const std::atomic<bool> *cancel = nullptr);
+    // the same loop body driven from outside, the way a manager drives a worker over its unit channel
+    // (workers.rs:46-71; flux-node/src/main.rs:60-75): begin_job = Scene::from_data + Camera::new on every GPU,
+    // render_unit = camera.render(&scene, unit) with the unit's rows sharded over the GPUs in interleaved tiles.
+    void begin_job(const SceneData &sd, const JobConfiguration &cfg);
+    bool has_job() const { return job_ != nullptr; }
+    WorkUnitResult render_unit(const WorkUnit &unit);
+    uint32_t job_image_width() const { return job_ ? job_->width : 0; }
 
   private:
+    struct ActiveJob {
+        Scene scene;
+        std::vector<Camera> cameras;   // one per GPU, same seed: identical sample sets everywhere
+        uint32_t width = 0, height = 0;
+    };
+    std::unique_ptr<ActiveJob> job_;
     std::vector<int> devices_;
     std::vector<std::unique_ptr<GpuContext>> contexts_;   // created with the worker, like LocalWorker::new builds its pool
     uint64_t seed_;

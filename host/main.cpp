@@ -2,9 +2,10 @@
 //
 //   fluxb200 <scene_file> [-r ROOT] [-d DEPTH] [-R COUNT] [-G GPUS] [--seed S] [--width W --height H] [-o FILE]
 //
-// -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node, -L,
-// -g and -t have no counterpart: the network workers are replaced by the GPUs of this box (-G), there is no
-// local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
+// -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node ADDRESS[:PORT]
+// renders on a fluxb200-node (or flux-node) process instead of the local GPUs, speaking the reference's network
+// protocol (workers.rs:118-245); one node, since a node ends the connection after a job.  -L, -g and -t have no
+// counterpart: there is no local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
 // (manager.rs:330) unless -o is given.  --dump-flat FILE writes the flattened scene (no GPU needed; used by the
 // tests to compare this loader with the Python mirror).
 #include <cstdio>
@@ -13,11 +14,12 @@
 #include <string>
 
 #include "fluxhost.hpp"
+#include "fluxnet.hpp"
 
 namespace {
 
 struct Config {   // flux/src/main.rs:114-124
-    std::string input_filename, output_filename, dump_flat;
+    std::string input_filename, output_filename, dump_flat, node;
     uint32_t sample_root = 1, max_depth = 5, rows_per_work_unit = 50;
     uint32_t gpus = 1, width = 0, height = 0;
     uint64_t seed = 1;
@@ -32,6 +34,7 @@ struct Config {   // flux/src/main.rs:114-124
                  "    -d, --depth <DEPTH>    Tracing depth [default: 5]\n"
                  "    -R, --rows <COUNT>     Image rows per work unit [default: 50]\n"
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
+                 "    -n, --node <ADDRESS[:PORT]>   Render using the fluxb200-node / flux-node process at this address\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
                  "        --width <W> --height <H>   Override the scene's image size\n"
                  "    -o <FILE>              Output file [default: <scene_name>.ppm]\n"
@@ -59,6 +62,7 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-d" || a == "--depth") c.max_depth = (uint32_t)parse_u64(next("--depth"), "--depth");
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
+        else if (a == "-n" || a == "--node") c.node = next("--node");
         else if (a == "--seed") c.seed = parse_u64(next("--seed"), "--seed");
         else if (a == "--width") c.width = (uint32_t)parse_u64(next("--width"), "--width");
         else if (a == "--height") c.height = (uint32_t)parse_u64(next("--height"), "--height");
@@ -74,52 +78,6 @@ Config config_from_args(int argc, char **argv) {
     return c;
 }
 
-// Flattened scene as text, doubles in hex-float so the comparison with the Python loader is exact.
-void dump_flat(const std::string &path, flux::FlatScene &f) {
-    FILE *o = std::fopen(path.c_str(), "w");
-    if (!o) throw flux::Error("cannot write `" + path + "`");
-    const flux_scene_flat &s = *f.ptr();
-    auto dv = [&](const char *name, const double *p, size_t n) {
-        std::fprintf(o, "%s %zu", name, n);
-        for (size_t i = 0; i < n; i++) std::fprintf(o, " %a", p[i]);
-        std::fprintf(o, "\n");
-    };
-    auto uv = [&](const char *name, const uint32_t *p, size_t n) {
-        std::fprintf(o, "%s %zu", name, n);
-        for (size_t i = 0; i < n; i++) std::fprintf(o, " %u", p[i]);
-        std::fprintf(o, "\n");
-    };
-    std::fprintf(o, "image %u %u\n", s.image_width, s.image_height);
-    const double scal[] = {s.pixel_size, s.zoom_factor, s.view_plane_distance, s.focal_distance, s.lens_radius};
-    dv("scalars", scal, 5);
-    dv("background", s.background, 3);
-    dv("eye", s.eye, 3);
-    dv("look_at", s.look_at, 3);
-    dv("up", s.up, 3);
-    std::fprintf(o, "materials %u\n", s.n_materials);
-    for (uint32_t i = 0; i < s.n_materials; i++) {
-        const flux_material &m = s.materials[i];
-        std::fprintf(o, "material %u %a %a %a %a %a\n", m.kind, m.color[0], m.color[1], m.color[2], m.k, m.exp);
-    }
-    dv("sphere_center", s.sphere_center, 3 * (size_t)s.n_spheres);
-    dv("sphere_radius", s.sphere_radius, s.n_spheres);
-    std::fprintf(o, "sphere_invert %u", s.n_spheres);
-    for (uint32_t i = 0; i < s.n_spheres; i++) std::fprintf(o, " %u", (unsigned)s.sphere_invert[i]);
-    std::fprintf(o, "\n");
-    uv("sphere_shape_id", s.sphere_shape_id, s.n_spheres);
-    uv("sphere_material", s.sphere_material, s.n_spheres);
-    dv("plane_point", s.plane_point, 3 * (size_t)s.n_planes);
-    dv("plane_normal", s.plane_normal, 3 * (size_t)s.n_planes);
-    uv("plane_shape_id", s.plane_shape_id, s.n_planes);
-    uv("plane_material", s.plane_material, s.n_planes);
-    dv("tri_v0", s.tri_v0, 3 * (size_t)s.n_triangles);
-    dv("tri_v1", s.tri_v1, 3 * (size_t)s.n_triangles);
-    dv("tri_v2", s.tri_v2, 3 * (size_t)s.n_triangles);
-    uv("tri_shape_id", s.tri_shape_id, s.n_triangles);
-    uv("tri_material", s.tri_material, s.n_triangles);
-    std::fclose(o);
-}
-
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -130,7 +88,22 @@ int main(int argc, char **argv) {
         if (config.width && config.height) s = s.with_size(config.width, config.height);
         if (!config.dump_flat.empty()) {
             auto flat = s.flatten();
-            dump_flat(config.dump_flat, *flat);
+            flux::dump_flat_text(config.dump_flat, *flat);
+            return 0;
+        }
+        flux::JobConfiguration netcfg;
+        netcfg.sample_root = config.sample_root;
+        netcfg.max_trace_depth = config.max_depth;
+        netcfg.rows_per_work_unit = config.rows_per_work_unit;
+        if (!config.node.empty()) {
+            flux::net::NetworkWorker node(config.node);
+            std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),
+                        netcfg.sample_root * netcfg.sample_root, netcfg.sample_root == 1 ? "" : "s", netcfg.max_trace_depth);
+            flux::Image img = node.render_job(flux::Job{flux::JobID{config.seed, 0}, s, netcfg});
+            std::printf("Network worker ready, info:\nThreads: %u\n", node.info().num_threads);
+            const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
+            img.write(out);
+            std::printf("wrote %s\nShutting down\n", out.c_str());
             return 0;
         }
         std::vector<int> devices;

@@ -1,0 +1,97 @@
+"""fluxb200-node on a real GPU: a manager speaking the reference's protocol (workers.rs:118-245) gets back exactly
+the rows the GPU worker renders locally.  Both clients are exercised: the Python NetworkWorker (independent codec)
+and the C++ one (`fluxb200 -n`)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from flux_b200 import JobConfiguration, SceneData, _capi
+from flux_b200 import netproto as N
+from flux_b200.worker import GpuWorker
+from tests import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def start_node(*extra):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "host"), "-s"], check=True)
+    p = subprocess.Popen([os.path.join(ROOT, "host", "fluxb200-node"), "-h", "127.0.0.1", "-p", "0", "--clients", "1", *extra],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    line = p.stdout.readline().decode()
+    assert line.startswith("Bind address: 127.0.0.1:"), (line, p.stderr.read().decode() if p.poll() is not None else "")
+    return p, int(line.rsplit(":", 1)[1])
+
+
+def test_python_manager_gets_the_rows_the_gpu_renders(gpu_ctx):
+    sd = Hp.deterministic_scene(96, 64)
+    cfg = JobConfiguration(4, 5, 10)
+    proc, port = start_node("--seed", "5")
+    try:
+        w = N.NetworkWorker(f"127.0.0.1:{port}", timeout=120)
+        assert w.info() == {"num_threads": 1}
+        img = w.render_job(sd, cfg, job_id=(2 ** 64 - 1, 9))
+        assert proc.wait(30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    log = proc.stdout.read().decode()
+    assert "Got connection from 127.0.0.1:" in log and "Got job" in log and "Got done message, shutting down" in log
+    local = GpuWorker(0, seed=5)
+    try:
+        ref = local.render_image(sd, cfg)
+    finally:
+        local.stop()
+    assert np.array_equal(img.view(np.uint64), ref.view(np.uint64))
+    assert float(ref.max()) > 0.1
+
+
+def test_cpp_manager_over_the_node_writes_the_local_ppm(tmp_path):
+    """`fluxb200 demo2.yml -n node` == `fluxb200 demo2.yml` byte for byte (same seed, glossy scene, depth of field)."""
+    cli = os.path.join(ROOT, "host", "fluxb200")
+    scene = os.path.join(ROOT, "scenes", "demo2.yml")
+    common = ["-r", "4", "-R", "9", "--width", "64", "--height", "48", "--seed", "3"]
+    proc, port = start_node("--seed", "3")
+    try:
+        a = subprocess.run([cli, scene, "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
+        assert a.returncode == 0, a.stderr.decode()
+        assert proc.wait(30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    b = subprocess.run([cli, scene, *common, "-o", str(tmp_path / "local.ppm")], capture_output=True, timeout=300)
+    assert b.returncode == 0, b.stderr.decode()
+    assert (tmp_path / "net.ppm").read_bytes() == (tmp_path / "local.ppm").read_bytes()
+
+
+def test_node_drops_a_client_that_breaks_the_protocol_and_serves_the_next():
+    import socket
+    proc, port = start_node_n(2)
+    try:
+        s = socket.create_connection(("127.0.0.1", port), timeout=30)
+        rf = s.makefile("rb")
+        assert N.load(lambda n: rf.read(n)) == {"num_threads": 1}
+        s.sendall(N.work_unit(N.WorkUnit(0, 3, (1, 1))))       # a unit before any job
+        assert rf.read(1) == b""                                # dropped
+        s.close()
+        sd = Hp.deterministic_scene(32, 16)
+        w = N.NetworkWorker(f"127.0.0.1:{port}", timeout=120)
+        img = w.render_job(sd, JobConfiguration(2, 5, 16))
+        assert img.shape == (16, 32, 3) and float(img.max()) > 0.1
+        assert proc.wait(30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    assert "handle_client exited with work unit before SetJob" in proc.stdout.read().decode()
+
+
+def start_node_n(n):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "host"), "-s"], check=True)
+    p = subprocess.Popen([os.path.join(ROOT, "host", "fluxb200-node"), "-h", "127.0.0.1", "-p", "0", "--clients", str(n)],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    line = p.stdout.readline().decode()
+    assert line.startswith("Bind address: 127.0.0.1:"), line
+    return p, int(line.rsplit(":", 1)[1])
