@@ -90,6 +90,8 @@ PROTOTYPES = {
     "flux_set_glossy_table": (C.c_int, [_ctx, C.c_int]),
     "flux_measure_fp64_peak": (C.c_int, [_ctx, _dp]),
     "flux_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _dp]),
+    "flux_progressive_begin": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_uint32]),
+    "flux_progressive_pass": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, _dp]),
 }
 
 # FLUXB200_LIB selects an alternative build of the same library (A/B of compile-time kernel variants)

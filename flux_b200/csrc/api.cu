@@ -61,7 +61,11 @@ struct flux_ctx {
     float last_ms = 0.f;
     uint64_t launches = 0;
 
-    DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink, ghemi, ginv;
+    DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink, ghemi, ginv, accum;
+    // progressive passes: the rows being refined and how many samples per pixel the accumulator holds
+    std::vector<uint32_t> prog_rows;
+    uint32_t prog_done = 0;
+    bool prog_active = false;
     std::vector<double> g_inv_e1;  // 1/(exp+1) of the distinct glossy exponents of the scene
     bool use_gtable = true;
     DevBuf<uint32_t> sph_meta, pln_meta, tri_meta, set_index, rows;
@@ -272,6 +276,7 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
 
     DeviceGuard g(ctx->device);
     ctx->have_scene = false;
+    ctx->prog_active = false;
     // ---- materials: per-material constants (same IEEE products as the reference) ----
     std::vector<DevMaterial> mats(s->n_materials);
     for (uint32_t i = 0; i < s->n_materials; i++) {
@@ -428,6 +433,7 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     // samples / set index belong to a job: a new scene invalidates them if shapes changed
     if (ctx->have_samples && (ctx->ss.root != cfg->sample_root || ctx->ss.max_depth != cfg->max_trace_depth))
         ctx->have_samples = false;
+        ctx->prog_active = false;
     if (ctx->have_index && ctx->set_index.cap < (size_t)cam.W * cam.H) ctx->have_index = false;
     if (ctx->have_samples) return build_glossy_table(ctx);  // exponents may have changed
     ctx->ss.ghemi = nullptr;
@@ -483,6 +489,7 @@ int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t 
     if ((uint64_t)root * root > 0xFFFFFFFFull) return fail(ctx, FLUX_ERR_INVALID, "flux_set_samples: root too large");
     DeviceGuard g(ctx->device);
     ctx->have_samples = false;
+    ctx->prog_active = false;
     int rc = alloc_samples(ctx, root, max_depth, num_sets);
     if (rc) return rc;
     const size_t n = (size_t)root * root;
@@ -505,6 +512,7 @@ int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
         return fail(ctx, FLUX_ERR_INVALID, "flux_generate_samples: num_sets too large (use flux_set_set_index)");
     DeviceGuard g(ctx->device);
     ctx->have_samples = false;
+    ctx->prog_active = false;
     ctx->have_index = false;
     int rc = alloc_samples(ctx, root, depth, num_sets);
     if (rc) return rc;
@@ -608,6 +616,9 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     p.work_counter = ctx->work_counter.p;
     std::memcpy(p.cull, ctx->cull, sizeof(p.cull));
     p.cull_cmax = ctx->cull_cmax;
+    p.i_begin = 0;
+    p.i_end = ctx->ss.n;
+    p.accum = nullptr;
     CK(cudaEventRecord(ctx->ev0, st));
     const bool regen_ok = regen_kernel_applicable(p);
     if (ctx->kernel_mode == 2 && !regen_ok)
@@ -655,6 +666,72 @@ int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     if (elems) CK(cudaMemcpyAsync(out_rgb, ctx->out.p, elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_rows) CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return FLUX_OK;
+}
+
+int flux_progressive_begin(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    ctx->prog_active = false;
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "progressive: scene not set");
+    if (n_rows && !rows) return fail(ctx, FLUX_ERR_INVALID, "progressive: null rows");
+    for (uint32_t k = 0; k < n_rows; k++) {
+        if (rows[k] >= ctx->cam.H) return fail(ctx, FLUX_ERR_INVALID, "progressive: row out of range");
+        if (k && rows[k] <= rows[k - 1]) return fail(ctx, FLUX_ERR_INVALID, "progressive: rows must be strictly ascending");
+    }
+    if ((uint64_t)n_rows * ctx->cam.W > 0xFFFFFFFFull) return fail(ctx, FLUX_ERR_INVALID, "progressive: too many pixels in one call");
+    DeviceGuard g(ctx->device);
+    const size_t elems = (size_t)n_rows * ctx->cam.W * 3;
+    CK(ctx->accum.reserve(elems));
+    CK(ctx->rows.reserve(n_rows));
+    if (elems) CK(cudaMemsetAsync(ctx->accum.p, 0, elems * sizeof(double), ctx->stream));
+    ctx->prog_rows.assign(rows, rows + n_rows);
+    ctx->prog_done = 0;
+    ctx->prog_active = true;
+    return FLUX_OK;
+}
+
+int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_end, double *out_rgb) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!ctx->prog_active) return fail(ctx, FLUX_ERR_STATE, "progressive: flux_progressive_begin not called (or the scene changed since)");
+    if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
+    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set");
+    if (sample_begin != ctx->prog_done) return fail(ctx, FLUX_ERR_INVALID, "progressive: passes must continue where the last one ended");
+    if (sample_end <= sample_begin || sample_end > ctx->ss.n) return fail(ctx, FLUX_ERR_INVALID, "progressive: bad sample range");
+    const uint32_t n_rows = (uint32_t)ctx->prog_rows.size();
+    if (n_rows == 0) return FLUX_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const uint32_t npix = n_rows * ctx->cam.W;
+    CK(cudaMemcpyAsync(ctx->rows.p, ctx->prog_rows.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->work_counter.p, 0, sizeof(unsigned int), st));
+    RenderParams p{};
+    p.scene = ctx->scene;
+    p.cam = ctx->cam;
+    p.ss = ctx->ss;
+    p.set_index = ctx->set_index.p;
+    p.rows = ctx->rows.p;
+    p.n_rows = n_rows;
+    p.out = nullptr;
+    p.counters = ctx->counters.p;
+    p.work_counter = ctx->work_counter.p;
+    p.i_begin = sample_begin;
+    p.i_end = sample_end;
+    p.accum = ctx->accum.p;
+    CK(cudaEventRecord(ctx->ev0, st));
+    launch_render(p, ctx->count, ctx->sm_count, st);
+    ctx->launches += 1;
+    ctx->prog_done = sample_end;
+    if (out_rgb) {
+        CK(ctx->out.reserve((size_t)npix * 3));
+        // 1 / count; with every sample in, exactly the reference's pixel_denom (trace.rs:59)
+        launch_resolve_accum(ctx->accum.p, ctx->out.p, npix, 1.0 / (double)sample_end, st);
+        ctx->launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaGetLastError());
+    if (out_rgb) CK(cudaMemcpyAsync(out_rgb, ctx->out.p, (size_t)npix * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return FLUX_OK;
 }
 

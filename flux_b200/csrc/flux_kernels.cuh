@@ -8,6 +8,7 @@
 
 // Camera::render for a list of rows (trace.rs:53-97).
 void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
+void launch_resolve_accum(const double *accum, double *out, uint32_t npix, double inv_count, cudaStream_t stream);
 
 // Same result, scheduled for high sample counts: warp per pixel, in-warp path regeneration,
 // scene in shared memory (render_regen.cu).

@@ -88,6 +88,10 @@ struct RenderParams {
     // non-finite) and for the unused entries.  cull_cmax >= max_k |centre_k| + radius over the valid spheres.
     float cull[FLUX_CULL_MAX][4];
     float cull_cmax;
+    // progressive passes (flux_progressive_pass, render.cu only): samples [i_begin, i_end) of every pixel; when
+    // `accum` is set their radiance sum is added to accum[n_rows][W][3] instead of being averaged into `out`
+    uint32_t i_begin, i_end;
+    double *accum;
 };
 
 // indices into flux_counters viewed as u64[]

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
             const uint32_t set = p.set_index[(size_t)row * W + col];
             const double2 *ps = p.ss.pixel + (size_t)set * n;
             const double2 *ds = p.ss.disc + (size_t)set * n;
-            for (uint32_t i = g; i < n; i += G) {
+            for (uint32_t i = p.i_begin + g; i < p.i_end; i += G) {
                 double2 s = ps[i];
                 double2 l = ds[i];
                 V3 o, d;
@@ -155,7 +155,12 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
             acc.g += __shfl_xor_sync(0xffffffffu, acc.g, off);
             acc.b += __shfl_xor_sync(0xffffffffu, acc.b, off);
         }
-        if (valid && g == 0) {  // trace.rs:85-86, color.rs:35-44
+        if (valid && g == 0 && p.accum) {  // progressive pass: the sum of this pass joins the sums of the earlier ones
+            double *a = p.accum + (size_t)pixel * 3;
+            a[0] += acc.r;
+            a[1] += acc.g;
+            a[2] += acc.b;
+        } else if (valid && g == 0) {  // trace.rs:85-86, color.rs:35-44
             double r = acc.r * pixel_denom, gg = acc.g * pixel_denom, b = acc.b * pixel_denom;
             double mx1 = r > gg ? r : gg;
             double mx2 = mx1 > b ? mx1 : b;
@@ -177,6 +182,28 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
     }
 }
 
+// the image of the samples accumulated so far: sum * (1 / count), then max_to_one (trace.rs:85-86, color.rs:35-44)
+__global__ void resolve_accum_kernel(const double *__restrict__ accum, double *__restrict__ out, uint32_t npix, double inv_count) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= npix) return;
+    double r = accum[(size_t)pixel * 3] * inv_count, gg = accum[(size_t)pixel * 3 + 1] * inv_count, b = accum[(size_t)pixel * 3 + 2] * inv_count;
+    const double mx1 = r > gg ? r : gg;
+    const double mx2 = mx1 > b ? mx1 : b;
+    if (mx2 > 1.0) {
+        const double inv = 1.0 / mx2;
+        r *= inv;
+        gg *= inv;
+        b *= inv;
+    }
+    out[(size_t)pixel * 3] = r;
+    out[(size_t)pixel * 3 + 1] = gg;
+    out[(size_t)pixel * 3 + 2] = b;
+}
+
+void launch_resolve_accum(const double *accum, double *out, uint32_t npix, double inv_count, cudaStream_t stream) {
+    if (npix) resolve_accum_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(accum, out, npix, inv_count);
+}
+
 static uint32_t group_width(uint32_t n) {
     uint32_t G = 1;
     while (G < n && G < 32) G <<= 1;
@@ -184,7 +211,7 @@ static uint32_t group_width(uint32_t n) {
 }
 
 void launch_render(const RenderParams &p, bool count, int sm_count, cudaStream_t stream) {
-    const uint32_t G = group_width(p.ss.n);
+    const uint32_t G = group_width(p.i_end - p.i_begin);
     const int threads = 256;
     const uint32_t ppw = 32 / G;
     const uint64_t npix = (uint64_t)p.n_rows * p.cam.W;

@@ -118,6 +118,17 @@ class GpuContext:
         self._ck(self._lib.flux_render_row_list_device(self._ctx, _capi.as_u32p(rows), rows.shape[0],
                                                        C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
 
+    def progressive_begin(self, rows):
+        rows = np.ascontiguousarray(rows, np.uint32)
+        self._prog_shape = rows.shape[0]
+        self._ck(self._lib.flux_progressive_begin(self._ctx, _capi.as_u32p(rows), rows.shape[0]))
+
+    def progressive_pass(self, sample_begin: int, sample_end: int, width: int, want_image: bool = True):
+        """Adds samples [sample_begin, sample_end) of every pixel; returns the image so far (or None)."""
+        out = np.empty((self._prog_shape, width, 3), np.float64) if want_image else None
+        self._ck(self._lib.flux_progressive_pass(self._ctx, sample_begin, sample_end, _capi.as_dp(out) if want_image else None))
+        return out
+
     def trace_rays(self, origins, dirs):
         o = np.ascontiguousarray(origins, np.float64).reshape(-1, 3)
         d = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
@@ -221,6 +232,23 @@ class Camera:
     def render(self, scene: Scene, work: WorkUnit) -> WorkUnitResult:
         rows = self.ctx.render_rows(work.row_start, work.row_end, self.width)
         return WorkUnitResult(work, rows)
+
+    def render_progressive(self, scene: Scene, work: WorkUnit, batch: int, cancel=None):
+        """Progressive refinement of one work unit: yields ``(samples_done, WorkUnitResult)``
+        after every pass of ``batch`` samples per pixel; the last one holds Camera::render's result (up to the
+        order of the per-pixel sum).  ``cancel()`` returning True stops before the next pass, like
+        JobHandle::cancel stops before the next work unit (manager.rs:66-69)."""
+        if batch < 1:
+            raise ValueError("batch must be >= 1")
+        n = self.config.sample_root ** 2
+        self.ctx.progressive_begin(np.arange(work.row_start, work.row_end + 1, dtype=np.uint32))
+        done = 0
+        while done < n:
+            if cancel is not None and cancel():
+                return
+            end = min(n, done + batch)
+            yield end, WorkUnitResult(work, self.ctx.progressive_pass(done, end, self.width))
+            done = end
 
 
 class GpuWorker:

@@ -693,6 +693,24 @@ std::vector<double> Camera::render_row_list(const std::vector<uint32_t> &rows) c
     return out;
 }
 
+WorkUnitResult Camera::render_progressive(const WorkUnit &unit, uint32_t sample_root, uint32_t batch,
+                                          const std::function<bool(uint32_t, const WorkUnitResult &)> &on_pass) const {
+    if (unit.row_end < unit.row_start) throw Error("Camera::render_progressive: row_end < row_start");
+    if (batch == 0) throw Error("Camera::render_progressive: batch must be >= 1");
+    std::vector<uint32_t> rows;
+    for (uint32_t r = unit.row_start; r <= unit.row_end; r++) rows.push_back(r);
+    ctx_->check(flux_progressive_begin(ctx_->get(), rows.data(), (uint32_t)rows.size()), "flux_progressive_begin");
+    WorkUnitResult r{unit, std::vector<double>(rows.size() * (size_t)width_ * 3)};
+    const uint32_t n = sample_root * sample_root;
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t end = std::min(n, done + batch);
+        ctx_->check(flux_progressive_pass(ctx_->get(), done, end, r.rows.data()), "flux_progressive_pass");
+        done = end;
+        if (on_pass && !on_pass(done, r)) break;
+    }
+    return r;
+}
+
 float Camera::last_kernel_ms() const {
     float ms = 0.f;
     flux_last_kernel_ms(ctx_->get(), &ms);

@@ -19,6 +19,7 @@
 #include <array>
 #include <atomic>
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -145,6 +146,11 @@ class Camera {
     static Camera create(GpuContext &ctx, const Scene &scene, const JobConfiguration &cfg, uint32_t num_sets, uint64_t seed);
     WorkUnitResult render(const Scene &scene, const WorkUnit &unit) const;
     std::vector<double> render_row_list(const std::vector<uint32_t> &rows) const;
+    // Progressive refinement of one work unit: passes of `batch` samples per pixel; after each
+    // pass `on_pass(samples_done, result_so_far)` is called and returns false to cancel (JobHandle::cancel,
+    // manager.rs:66-69, between passes instead of between work units).  Returns the last result.
+    WorkUnitResult render_progressive(const WorkUnit &unit, uint32_t sample_root, uint32_t batch,
+                                      const std::function<bool(uint32_t, const WorkUnitResult &)> &on_pass) const;
     float last_kernel_ms() const;
 
   private:

@@ -202,6 +202,19 @@ int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx /* [image_height][imag
 int flux_render_rows(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive,
                      double *out_rgb /* host */);
 
+/* Progressive refinement (the reference's preview re-renders the whole job at another sample
+ * root, flux/src/main.rs:296-315, and cancels between work units, manager.rs:66-69).  flux_progressive_begin
+ * names the rows (strictly ascending) and clears their accumulator; each flux_progressive_pass traces samples
+ * [sample_begin, sample_end) of every pixel of those rows — the same sample sets, set-index map and per-sample
+ * arithmetic as Camera::render (trace.rs:53-97) — and adds their radiance to the accumulator.  Passes must follow
+ * one another (sample_begin = the previous sample_end, 0 first; sample_end <= sample_root^2).  out_rgb (host,
+ * [n_rows][image_width][3], may be NULL) receives the image of the samples so far: sum * (1 / sample_end), then
+ * max_to_one.  After the last pass that is Camera::render's result up to the order of the per-pixel sum; one pass
+ * over all samples is bit-identical to flux_render_rows with kernel mode 1.  The caller cancels by not issuing the
+ * next pass.  flux_set_scene and the sample-set calls end a progression. */
+int flux_progressive_begin(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows);
+int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_end, double *out_rgb /* host or NULL */);
+
 /* Same, writing to device memory on `cuda_stream` (a cudaStream_t, may be NULL)
  * without synchronising: for callers that keep the framebuffer on the GPU
  * (multi-GPU gather over NVLink). */
