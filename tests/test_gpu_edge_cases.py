@@ -1,0 +1,141 @@
+"""Edge cases of the render path against the oracle: empty and one-shape scenes, 1-pixel and 1-row images, single
+samples, NaN pixels, colours above one, zero rows, and the largest sizes — at sizes the oracle cannot render, through
+properties that do not depend on the size (sharding, row subsets, pass accumulation)."""
+import numpy as np
+import pytest
+
+from flux_b200 import (CameraData, CameraSettings, Emissive, JobConfiguration, Matte, OutputSettings, PlaneData, Reflective,
+                       SceneData, SphereData)
+from oracle import oracle_py as O
+from tests import helpers as Hp
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(shapes, width, height, background=(0.1, 0.2, 0.3), eye=(0.0, 3.0, -9.0), lens=0.0):
+    return SceneData("edge", OutputSettings(width, height, 0.5), background, shapes,
+                     CameraSettings(eye, (0.0, 1.0, 0.0), (0.0, 1.0, 0.0)), CameraData(6.0 * width / 800.0, 500.0, 10.0, lens))
+
+
+def _modes_for(cfg):
+    spp = cfg.sample_root ** 2
+    return [m for m, need in ((1, 1), (2, 64), (4, 256)) if spp >= need]
+
+
+def _check_all_modes(gpu_ctx, sd, cfg, seed=3, tol=1e-12):
+    w, h = sd.output_settings.image_width, sd.output_settings.image_height
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(seed, cfg, w, h)
+    ref = O.render_rows(flat, cfg, ss, 0, h - 1)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    try:
+        for mode in [0] + _modes_for(cfg):
+            gpu_ctx.set_kernel_mode(mode)
+            img = gpu_ctx.render_rows(0, h - 1, w)
+            assert Hp.rel_err(img, ref) <= tol, mode
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+    return ref
+
+
+@pytest.mark.parametrize("root", [1, 8, 16])
+def test_scene_without_shapes_is_the_background(gpu_ctx, root):
+    ref = _check_all_modes(gpu_ctx, _scene([], 12, 9), JobConfiguration(root, 5, 50))
+    assert np.allclose(ref, [0.1, 0.2, 0.3], rtol=1e-12)
+
+
+@pytest.mark.parametrize("root", [1, 16])
+def test_background_above_one_is_scaled_by_max_to_one(gpu_ctx, root):
+    ref = _check_all_modes(gpu_ctx, _scene([], 5, 4, background=(4.0, 2.0, 1.0)), JobConfiguration(root, 5, 50))
+    assert np.allclose(ref, [1.0, 0.5, 0.25], rtol=1e-12)       # color.rs:35-44
+
+
+@pytest.mark.parametrize("width,height", [(1, 1), (1, 7), (9, 1), (33, 2)])
+def test_tiny_images_every_kernel(gpu_ctx, width, height):
+    shapes = [SphereData((0, 0, 0), 100.0, Emissive((1, 0.9, 0.8), 0.6), True),
+              SphereData((0.0, 1.0, 0.0), 1.5, Matte((0.6, 0.6, 0.6), (1, 1, 1), 1.0), False),
+              PlaneData((0, 0, 0), (0, 1, 0), Reflective(0.8, (0.9, 0.9, 0.9)))]
+    _check_all_modes(gpu_ctx, _scene(shapes, width, height, lens=0.1), JobConfiguration(16, 5, 50))
+
+
+def test_only_planes_and_only_one_sphere(gpu_ctx):
+    plane = PlaneData((0, 0, 0), (0, 1, 0), Matte((0.5, 0.5, 0.5), (1, 1, 1), 1.0))
+    _check_all_modes(gpu_ctx, _scene([plane, PlaneData((0, 9, 0), (0, -1, 0), Emissive((1, 1, 1), 2.0))], 16, 12), JobConfiguration(16, 5, 50))
+    _check_all_modes(gpu_ctx, _scene([SphereData((0, 1, 0), 2.0, Emissive((1, 0.5, 0.2), 3.0), False)], 16, 12), JobConfiguration(16, 5, 50))
+
+
+def test_nan_and_infinite_radiance_coincide_with_the_oracle(gpu_ctx):
+    """An emitter of infinite power gives inf radiance, which max_to_one turns into inf * (1 / inf) = NaN
+    (color.rs:35-44); a NaN colour component poisons its channel only.  Whatever the reference's arithmetic yields,
+    the GPU yields the same pattern (rel_err requires the NaN masks to coincide).  Degenerate shapes ride along: a
+    zero-radius sphere (its box is never passed: t0 < t1 fails) and a plane with a null normal (t = 0/0 is no hit)."""
+    shapes = [SphereData((0, 0, 0), 50.0, Emissive((1, 1, 1), 0.5), True),
+              SphereData((-1.5, 1.0, 0.0), 0.8, Emissive((1.0, 0.5, 0.25), float("inf")), False),
+              SphereData((1.5, 1.0, 0.0), 0.8, Emissive((0.5, float("nan"), 0.25), 2.0), False),
+              SphereData((0.0, 1.0, 0.0), 0.0, Matte((0.6, 0.6, 0.6), (1, 1, 1), 1.0), False),
+              PlaneData((0, 5, 0), (0, 0, 0), Matte((0.5, 0.5, 0.5), (1, 1, 1), 1.0)),
+              PlaneData((0, 0, 0), (0, 1, 0), Matte((0.5, 0.5, 0.5), (1, 1, 1), 1.0))]
+    sd = _scene(shapes, 24, 16)
+    ref = _check_all_modes(gpu_ctx, sd, JobConfiguration(16, 5, 50))
+    nan = np.isnan(ref)
+    assert nan.any() and not nan.all()
+    assert (nan[..., 1] & ~nan[..., 0]).any()        # the NaN green channel alone, somewhere on the right sphere
+
+
+def test_zero_rows_and_single_rows(gpu_ctx):
+    sd = Hp.deterministic_scene(32, 16)
+    cfg = JobConfiguration(4, 5, 50)
+    Hp.upload(gpu_ctx, sd.flatten(), cfg, Hp.oracle_samples(2, cfg, 32, 16))
+    assert gpu_ctx.render_row_list(np.zeros(0, np.uint32), 32).shape == (0, 32, 3)
+    full = gpu_ctx.render_rows(0, 15, 32)
+    for r in (0, 7, 15):
+        assert np.array_equal(gpu_ctx.render_rows(r, r, 32).view(np.uint64), full[r:r + 1].view(np.uint64))
+    picked = gpu_ctx.render_row_list(np.array([1, 2, 9, 15], np.uint32), 32)
+    assert np.array_equal(picked.view(np.uint64), full[[1, 2, 9, 15]].view(np.uint64))
+
+
+def test_largest_sample_count_on_a_few_pixels(gpu_ctx):
+    """sample_root 160 (25 600 spp, beyond BASELINE config 2's 16 384) on a 4x3 image: the wavefront kernel against
+    the oracle, which still finishes in seconds at this pixel count."""
+    sd = Hp.deterministic_scene(4, 3)
+    cfg = JobConfiguration(160, 5, 50)
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(8, cfg, 4, 3)
+    ref = O.render_rows(flat, cfg, ss, 0, 2)
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    img = gpu_ctx.render_rows(0, 2, 4)
+    assert Hp.rel_err(img, ref) <= 1e-11
+
+
+def test_largest_image_through_size_independent_properties(gpu_ctx):
+    """4096 x 2304 (9.4 M pixels, 85 M samples at 9 spp; the oracle would need minutes): rows rendered alone, in
+    shards of interleaved tiles and as progressive passes must be the very pixels of the full render; two whole rows
+    from the middle of the frame are checked against the oracle as well."""
+    from flux_b200.worker import shard_rows
+    w, h = 4096, 2304
+    sd = Hp.deterministic_scene(w, h)
+    cfg = JobConfiguration(3, 5, 50)
+    gpu_ctx.set_scene(sd.flatten(), cfg)
+    gpu_ctx.generate_samples(11, w)
+    full = gpu_ctx.render_rows(0, h - 1, w)
+    assert np.isfinite(full).all() and 0.0 <= full.min() and full.max() <= 1.0 and full.std() > 0.05
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(h, 40, replace=False)).astype(np.uint32)
+    assert np.array_equal(gpu_ctx.render_row_list(rows, w).view(np.uint64), full[rows].view(np.uint64))
+    parts = np.empty_like(full)
+    for rank in range(3):
+        mine = shard_rows(h, 4, rank, 3)
+        parts[mine] = gpu_ctx.render_row_list(mine, w)
+    assert np.array_equal(parts.view(np.uint64), full.view(np.uint64))
+    gpu_ctx.set_kernel_mode(1)
+    try:
+        band = gpu_ctx.render_rows(1000, 1099, w)
+        gpu_ctx.progressive_begin(np.arange(1000, 1100, dtype=np.uint32))
+        gpu_ctx.progressive_pass(0, 4, w, want_image=False)
+        assert Hp.rel_err(gpu_ctx.progressive_pass(4, 9, w), band) <= 1e-12
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+    ss_o = O.generate_samples(11, 3, 5, w)
+    ss_o.set_index = O.generate_set_index(11, h, w, w)
+    ref = O.render_rows(sd.flatten(), cfg, ss_o, 1152, 1153)
+    assert Hp.rel_err(full[1152:1154], ref) <= 1e-12
