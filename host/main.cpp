@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "fluxhost.hpp"
 #include "fluxnet.hpp"
@@ -23,6 +24,7 @@ struct Config {   // flux/src/main.rs:114-124
     uint32_t sample_root = 1, max_depth = 5, rows_per_work_unit = 50;
     uint32_t gpus = 1, width = 0, height = 0;
     uint64_t seed = 1;
+    std::vector<int> devices;
 };
 
 [[noreturn]] void usage(const char *msg) {
@@ -34,6 +36,7 @@ struct Config {   // flux/src/main.rs:114-124
                  "    -d, --depth <DEPTH>    Tracing depth [default: 5]\n"
                  "    -R, --rows <COUNT>     Image rows per work unit [default: 50]\n"
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
+                 "        --devices <LIST>   Explicit CUDA device list instead of -G, e.g. 0,2,3\n"
                  "    -n, --node <ADDRESS[:PORT]>   Render using the fluxb200-node / flux-node process at this address\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
                  "        --width <W> --height <H>   Override the scene's image size\n"
@@ -63,7 +66,14 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
         else if (a == "-n" || a == "--node") c.node = next("--node");
-        else if (a == "--seed") c.seed = parse_u64(next("--seed"), "--seed");
+        else if (a == "--devices") {   // explicit device list, e.g. 0,0 = two contexts on one GPU (tests of the sharded path)
+            for (const char *p = next("--devices"); *p;) {
+                char *end = nullptr;
+                c.devices.push_back((int)std::strtol(p, &end, 10));
+                if (end == p) usage("invalid value for --devices");
+                p = *end == ',' ? end + 1 : end;
+            }
+        } else if (a == "--seed") c.seed = parse_u64(next("--seed"), "--seed");
         else if (a == "--width") c.width = (uint32_t)parse_u64(next("--width"), "--width");
         else if (a == "--height") c.height = (uint32_t)parse_u64(next("--height"), "--height");
         else if (a == "-o") c.output_filename = next("-o");
@@ -106,8 +116,9 @@ int main(int argc, char **argv) {
             std::printf("wrote %s\nShutting down\n", out.c_str());
             return 0;
         }
-        std::vector<int> devices;
-        for (uint32_t g = 0; g < config.gpus; g++) devices.push_back((int)g);
+        std::vector<int> devices = config.devices;
+        if (devices.empty())
+            for (uint32_t g = 0; g < config.gpus; g++) devices.push_back((int)g);
         flux::GpuWorker worker(devices, config.seed);
         std::printf("GPU worker ready, info:\n");
         std::printf("Threads: %u\n", worker.info().num_threads);   // WorkerInfo::print, manager.rs:227-229
@@ -121,7 +132,7 @@ int main(int argc, char **argv) {
         flux::Image img = worker.render_job(s, jobcfg, &seconds);
         std::printf("rendering finished, total time %.6fs\n", seconds);   // manager.rs:327
         const double n = (double)img.width * img.height * jobcfg.sample_root * jobcfg.sample_root;
-        std::printf("%.1f Msamples/s on %u GPU(s)\n", n / seconds / 1e6, config.gpus);
+        std::printf("%.1f Msamples/s on %u GPU(s)\n", n / seconds / 1e6, (unsigned)devices.size());
         const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
         img.write(out);
         std::printf("wrote %s\n", out.c_str());

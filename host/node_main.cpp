@@ -33,6 +33,7 @@ namespace {
                  "    -h, --host <ADDRESS>   Listen for requests on this address [default: 0.0.0.0]\n"
                  "    -p, --port <PORT>      Listen on this TCP port [default: 2000]\n"
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
+                 "        --devices <LIST>   Explicit CUDA device list instead of -G, e.g. 0,2,3\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
                  "        --clients <N>      Exit after serving N connections [default: serve forever]\n"
                  "        --decode <FILE> | --reencode <FILE> | --rows-ready <5 integers>   codec tools, see the source\n");
@@ -104,6 +105,7 @@ int main(int argc, char **argv) {
     std::string host = "0.0.0.0", port = flux::net::DEFAULT_PORT;
     uint32_t gpus = 1;
     uint64_t seed = 1, clients = 0;
+    std::vector<int> devices;
     try {
         for (int i = 1; i < argc; i++) {
             const std::string a = argv[i];
@@ -115,7 +117,14 @@ int main(int argc, char **argv) {
             else if (a == "-p" || a == "--port") port = next("--port");
             else if (a == "-t" || a == "--threads") next("--threads");
             else if (a == "-G" || a == "--gpus") gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
-            else if (a == "--seed") seed = parse_u64(next("--seed"), "--seed");
+            else if (a == "--devices") {   // explicit device list, e.g. 0,0 = two contexts on one GPU (tests of the sharded path)
+                for (const char *p = next("--devices"); *p;) {
+                    char *end = nullptr;
+                    devices.push_back((int)std::strtol(p, &end, 10));
+                    if (end == p) usage("invalid value for --devices");
+                    p = *end == ',' ? end + 1 : end;
+                }
+            } else if (a == "--seed") seed = parse_u64(next("--seed"), "--seed");
             else if (a == "--clients") clients = parse_u64(next("--clients"), "--clients");
             else if (a == "--decode") return codec_requests(next("--decode"), false);
             else if (a == "--reencode") return codec_requests(next("--reencode"), true);
@@ -134,8 +143,8 @@ int main(int argc, char **argv) {
             else usage(("unknown option " + a).c_str());
         }
         if (gpus == 0) usage("--gpus must be >= 1");
-        std::vector<int> devices;
-        for (uint32_t g = 0; g < gpus; g++) devices.push_back((int)g);
+        if (devices.empty())
+            for (uint32_t g = 0; g < gpus; g++) devices.push_back((int)g);
         flux::GpuWorker worker(devices, seed);   // fails loudly without a GPU: there is no CPU rendering path
         flux::net::NodeServer server(worker, host, port);
         std::printf("Bind address: %s:%u\n", host.c_str(), (unsigned)server.port());   // flux-node/src/main.rs:159

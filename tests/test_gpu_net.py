@@ -95,3 +95,28 @@ def start_node_n(n):
     line = p.stdout.readline().decode()
     assert line.startswith("Bind address: 127.0.0.1:"), line
     return p, int(line.rsplit(":", 1)[1])
+
+
+def test_sharded_worker_paths_render_the_same_pixels(tmp_path):
+    """Two contexts (here on the same GPU, `--devices 0,0`) exercise the multi-GPU paths of the C++ host: work units
+    sharded in interleaved tiles by the node (GpuWorker::render_unit) and the whole frame sharded by the driver
+    (GpuWorker::render_job).  Pixels must not depend on the sharding."""
+    cli = os.path.join(ROOT, "host", "fluxb200")
+    scene = os.path.join(ROOT, "scenes", "demo2.yml")
+    common = ["-r", "4", "-R", "11", "--width", "64", "--height", "50", "--seed", "8"]
+    one = subprocess.run([cli, scene, *common, "-o", str(tmp_path / "one.ppm")], capture_output=True, timeout=300)
+    assert one.returncode == 0, one.stderr.decode()
+    two = subprocess.run([cli, scene, *common, "--devices", "0,0,0", "-o", str(tmp_path / "three.ppm")], capture_output=True, timeout=300)
+    assert two.returncode == 0, two.stderr.decode()
+    assert b"on 3 GPU(s)" in two.stdout
+    assert (tmp_path / "three.ppm").read_bytes() == (tmp_path / "one.ppm").read_bytes()
+    proc, port = start_node("--seed", "8", "--devices", "0,0")
+    try:
+        net = subprocess.run([cli, scene, "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
+        assert net.returncode == 0, net.stderr.decode()
+        assert b"Threads: 2" in net.stdout
+        assert proc.wait(30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    assert (tmp_path / "net.ppm").read_bytes() == (tmp_path / "one.ppm").read_bytes()
