@@ -633,7 +633,16 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     // spheres: 2.72 vs 1.90 Gsamples/s), the regeneration kernel on deep trees whose traversal lengths vary a lot
     // (config 3, 1 M triangles: 567 vs 426 Msamples/s)
     const bool wave2_auto = wave2_ok && (!p.scene.use_bvh || p.scene.bvh_n_nodes <= 1024);
-    if ((wave2_auto && ctx->kernel_mode == 0) || (wave2_ok && ctx->kernel_mode == 4))
+    // ... and on sphere/plane scenes the wavefront kernel's FP32-culled linear scan beats its own BVH owner stage up
+    // to about 120 spheres (measured r1, config-4 scene with 40 / 85 / 125 spheres: 5.21 vs 2.69, 2.98 vs 2.34, 2.29 vs
+    // 2.32 Gsamples/s), so a BVH built for the other kernels is left aside here unless it was asked for
+    RenderParams q = p;
+    q.scene.use_bvh = 0;
+    const bool wave2_linear = ctx->accel_mode == 0 && p.scene.use_bvh && p.scene.n_tris == 0 &&
+                              p.scene.n_spheres <= FLUX_WAVE2_LINEAR_MAX && wave2_kernel_applicable(q);
+    if (wave2_linear && (ctx->kernel_mode == 0 || ctx->kernel_mode == 4))
+        launch_render_wave2(q, ctx->count, ctx->sm_count, st);
+    else if ((wave2_auto && ctx->kernel_mode == 0) || (wave2_ok && ctx->kernel_mode == 4))
         launch_render_wave2(p, ctx->count, ctx->sm_count, st);
     else if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
         launch_render_wave(p, ctx->count, ctx->sm_count, st);

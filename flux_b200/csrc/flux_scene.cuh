@@ -72,6 +72,7 @@ struct DevSamples {
 };
 
 #define FLUX_CULL_MAX 128  // spheres covered by the constant-bank FP32 table (render_wave2.cu)
+#define FLUX_WAVE2_LINEAR_MAX 112  // up to here render_wave2.cu scans linearly even when a BVH exists (api.cu)
 
 struct RenderParams {
     DevScene scene;

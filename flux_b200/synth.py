@@ -58,7 +58,7 @@ def mesh_scene(nx: int = 1000, nz: int = 500, seed: int = 3, width: int = 800, h
                      CameraData(1.0, 500.0, 10.0, 0.09))
 
 
-def glossy_scene(width: int = 1920, height: int = 1080, seed: int = 4) -> SceneData:
+def glossy_scene(width: int = 1920, height: int = 1080, seed: int = 4, grid: int = 8) -> SceneData:
     """Config 4: area-light + reflective/glossy multi-bounce scene with divergent shading: an 8x8 jittered grid of
     unit spheres whose materials cycle Matte / Glossy(10) / Glossy(100) / Glossy(10000) / Reflective, two emissive
     sphere lights (power 10, r = 3), an inverted environment sphere (power 0.3), a matte floor; lens radius 0.09.
@@ -77,11 +77,11 @@ def glossy_scene(width: int = 1920, height: int = 1080, seed: int = 4) -> SceneD
         SphereData((14.0, 12.0, 10.0), 3.0, Emissive(_ENV_COLOR, 10.0), False),
     ]
     k = 0
-    for gx in range(8):
-        for gz in range(8):
+    for gx in range(grid):   # config 4 is the 8 x 8 grid; other sizes serve the linear-scan / BVH break-even measurements
+        for gz in range(grid):
             jx, jz = rng.uniform(-0.35, 0.35, 2)
             col = tuple(float(v) for v in rng.uniform(0.45, 1.0, 3))
-            shapes.append(SphereData((float((gx - 3.5) * 2.9 + jx), 1.0, float(gz * 2.9 + jz - 2.0)), 1.0, mats[k % 5](col), False))
+            shapes.append(SphereData((float((gx - (grid - 1) / 2) * 2.9 + jx), 1.0, float(gz * 2.9 + jz - 2.0)), 1.0, mats[k % 5](col), False))
             k += 1
     shapes.append(PlaneData((0.0, 0.0, 0.0), (0.0, 1.0, 0.0), Matte((0.5, 0.5, 0.5), (1.0, 1.0, 1.0), 1.0)))
     return SceneData("glossy64", OutputSettings(width, height, 0.5 * 1920.0 / width), (0.0, 0.0, 0.0), shapes,

@@ -75,11 +75,13 @@ def c5(ctx, n_total=100_000_000, chunk=10_000_000):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--mode=")]
+    args = [a for a in sys.argv[1:] if not a.startswith("--mode=") and not a.startswith("--accel=")]
+    accel = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--accel=")), 0)
     mode = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--mode=")), 0)
     which = set(args) or {"c1", "c3", "c4", "c5"}
     ctx = GpuContext(0)
     ctx.set_kernel_mode(mode)   # 0 = auto; A/B of render kernels on the same config
+    ctx.set_accel_mode(accel)   # 0 = auto, 1 = linear scan, 2 = BVH
     if "c1" in which:
         sd = SceneData.from_yaml(os.path.join(ROOT, "scenes", "demo1.yml")).with_size(512, 512)
         render_config(ctx, "c1 demo1 512x512 @16spp", sd, 4, reps=5)
@@ -89,6 +91,10 @@ def main():
         render_config(ctx, "c3 1M-triangle mesh 800x600 @1024spp (BVH)", synth.mesh_scene(1000, 500, seed=3), 32)
     if "c4" in which:
         render_config(ctx, "c4 glossy 1920x1080 @4096spp", synth.glossy_scene(), 64)
+    for a in sorted(which):   # c4gN: the config-4 scene with an N x N sphere grid at 960x540 (linear-scan / BVH break-even)
+        if a.startswith("c4g"):
+            g = int(a[3:])
+            render_config(ctx, f"c4 scene, {g}x{g} grid, 960x540 @4096spp", synth.glossy_scene(960, 540, grid=g), 64)
     ctx.close()
 
 
