@@ -9,8 +9,11 @@ This module is written independently of ``host/cbor.cpp`` / ``host/fluxnet.cpp``
 ``fluxb200-node``): a small RFC 7049 codec, the serde tree of the reference's data types, and a ``NetworkWorker``
 that drives any node speaking the protocol.  The tests pit the two implementations against each other and against
 hand-derived byte vectors; the Rust reference itself cannot be built in this image, so serde_cbor's choices (structs
-as text-keyed maps in declaration order, externally tagged enums as one-entry maps, unit variants as text, f64
-narrowed to f32 / f16 when exact) are taken from its documented behaviour.  Nothing here renders.
+as text-keyed maps in declaration order, unit variants as text, f64 narrowed to f32 when exact and to f16 for NaN /
+infinities) are taken from its documented behaviour.  Newtype enum variants have two forms: the 2-array
+``[name, content]`` that serde_cbor < 0.10 writes (the reference pins 0.9.0) and the one-entry map
+``{name: content}`` of 0.10 and later, which also read the older form.  ``form="array"`` is therefore the default for
+everything sent; both are accepted on input.  Nothing here renders.
 """
 from __future__ import annotations
 
@@ -195,46 +198,68 @@ def _color(c) -> dict:  # color.rs:12-16
     return {"r": float(c[0]), "g": float(c[1]), "b": float(c[2])}
 
 
-def material_tree(m) -> dict:  # shapes.rs:42-82
+def variant(name: str, content, form: str = "array"):
+    """A newtype enum variant in serde_cbor's array form (< 0.10) or map form (>= 0.10)."""
+    if form == "array":
+        return [name, content]
+    if form == "map":
+        return {name: content}
+    raise ValueError("form must be 'array' or 'map'")
+
+
+def variant_parts(x):
+    """(name, content) of an enum value in either form; a unit variant has content None."""
+    if isinstance(x, str):
+        return x, None
+    if isinstance(x, dict) and len(x) == 1:
+        (k, v), = x.items()
+        return k, v
+    if isinstance(x, list) and 1 <= len(x) <= 2 and isinstance(x[0], str):
+        return x[0], (x[1] if len(x) == 2 else None)
+    raise CborError(f"not an enum value: {str(x)[:80]}")
+
+
+def material_tree(m, form: str = "array"):  # shapes.rs:42-82
+    V = lambda name, content: variant(name, content, form)
     if isinstance(m, Matte):
-        return {"Matte": {"diffuse_color": _color(m.diffuse_color), "ambient_color": _color(m.ambient_color),
-                          "diffuse_coefficient": float(m.diffuse_coefficient)}}
+        return V("Matte", {"diffuse_color": _color(m.diffuse_color), "ambient_color": _color(m.ambient_color),
+                          "diffuse_coefficient": float(m.diffuse_coefficient)})
     if isinstance(m, Emissive):
-        return {"Emissive": {"color": _color(m.color), "power": float(m.power)}}
+        return V("Emissive", {"color": _color(m.color), "power": float(m.power)})
     if isinstance(m, Reflective):
-        return {"Reflective": {"reflect_amount": float(m.reflect_amount), "reflect_color": _color(m.reflect_color)}}
+        return V("Reflective", {"reflect_amount": float(m.reflect_amount), "reflect_color": _color(m.reflect_color)})
     if isinstance(m, GlossyReflective):
-        return {"GlossyReflective": {"reflect_amount": float(m.reflect_amount), "reflect_color": _color(m.reflect_color),
-                                     "reflect_exponent": float(m.reflect_exponent)}}
+        return V("GlossyReflective", {"reflect_amount": float(m.reflect_amount), "reflect_color": _color(m.reflect_color),
+                                      "reflect_exponent": float(m.reflect_exponent)})
     raise TypeError(type(m))
 
 
-def shape_tree(s) -> dict:  # scene.rs:71-74, shapes.rs:18-37 (+ extensions)
+def shape_tree(s, form: str = "array"):  # scene.rs:71-74, shapes.rs:18-37 (+ extensions)
+    V = lambda name, content: variant(name, content, form)
+    M = lambda m: material_tree(m, form)
     if isinstance(s, SphereData):
-        return {"Sphere": {"center": _v3(s.center), "radius": float(s.radius), "material": material_tree(s.material),
-                           "invert": bool(s.invert)}}
+        return V("Sphere", {"center": _v3(s.center), "radius": float(s.radius), "material": M(s.material), "invert": bool(s.invert)})
     if isinstance(s, PlaneData):
-        return {"Plane": {"point": _v3(s.point), "normal": _v3(s.normal), "material": material_tree(s.material)}}
+        return V("Plane", {"point": _v3(s.point), "normal": _v3(s.normal), "material": M(s.material)})
     if isinstance(s, TriangleData):
-        return {"Triangle": {"v0": _v3(s.v0), "v1": _v3(s.v1), "v2": _v3(s.v2), "material": material_tree(s.material)}}
+        return V("Triangle", {"v0": _v3(s.v0), "v1": _v3(s.v1), "v2": _v3(s.v2), "material": M(s.material)})
     if isinstance(s, MeshData):
-        return {"Mesh": {"vertices": [_v3(v) for v in np.asarray(s.vertices)],
-                         "faces": [[int(i) for i in f] for f in np.asarray(s.faces)], "material": material_tree(s.material)}}
+        return V("Mesh", {"vertices": [_v3(v) for v in np.asarray(s.vertices)],
+                          "faces": [[int(i) for i in f] for f in np.asarray(s.faces)], "material": M(s.material)})
     if isinstance(s, RectangleData):
-        return {"Rectangle": {"corner": _v3(s.corner), "edge_a": _v3(s.edge_a), "edge_b": _v3(s.edge_b),
-                              "material": material_tree(s.material)}}
+        return V("Rectangle", {"corner": _v3(s.corner), "edge_a": _v3(s.edge_a), "edge_b": _v3(s.edge_b), "material": M(s.material)})
     if isinstance(s, BoxData):
-        return {"Box": {"min": _v3(s.min), "max": _v3(s.max), "material": material_tree(s.material)}}
+        return V("Box", {"min": _v3(s.min), "max": _v3(s.max), "material": M(s.material)})
     raise TypeError(type(s))
 
 
-def scene_tree(sd: SceneData) -> dict:  # scene.rs:42-49
+def scene_tree(sd: SceneData, form: str = "array") -> dict:  # scene.rs:42-49
     o, cs, cd = sd.output_settings, sd.camera_settings, sd.camera_data
     return {"scene_name": sd.scene_name,
             "output_settings": {"image_width": int(o.image_width), "image_height": int(o.image_height),
                                 "pixel_size": float(o.pixel_size)},
             "background": _color(sd.background),
-            "shapes": [shape_tree(s) for s in sd.shapes],
+            "shapes": [shape_tree(s, form) for s in sd.shapes],
             "camera_settings": {"eye": _v3(cs.eye), "look_at": _v3(cs.look_at), "up": _v3(cs.up)},
             "camera_data": {"zoom_factor": float(cd.zoom_factor), "view_plane_distance": float(cd.view_plane_distance),
                             "focal_distance": float(cd.focal_distance), "lens_radius": float(cd.lens_radius)}}
@@ -244,14 +269,18 @@ def work_unit_tree(u: WorkUnit) -> dict:  # job.rs:40-44; JobID(usize, usize) is
     return {"row_start": int(u.row_start), "row_end": int(u.row_end), "job_id": [int(u.job_id[0]), int(u.job_id[1])]}
 
 
-def set_job(job_id: Tuple[int, int], sd: SceneData, cfg: JobConfiguration) -> bytes:
-    return dumps({"SetJob": {"id": [int(job_id[0]), int(job_id[1])], "scene_data": scene_tree(sd),
-                             "config": {"sample_root": int(cfg.sample_root), "max_trace_depth": int(cfg.max_trace_depth),
-                                        "rows_per_work_unit": int(cfg.rows_per_work_unit)}}})
+def job_tree(job_id: Tuple[int, int], sd: SceneData, cfg: JobConfiguration, form: str = "array") -> dict:  # job.rs:58-62
+    return {"id": [int(job_id[0]), int(job_id[1])], "scene_data": scene_tree(sd, form),
+            "config": {"sample_root": int(cfg.sample_root), "max_trace_depth": int(cfg.max_trace_depth),
+                       "rows_per_work_unit": int(cfg.rows_per_work_unit)}}
 
 
-def work_unit(u: WorkUnit) -> bytes:
-    return dumps({"WorkUnit": work_unit_tree(u)})
+def set_job(job_id: Tuple[int, int], sd: SceneData, cfg: JobConfiguration, form: str = "array") -> bytes:
+    return dumps(variant("SetJob", job_tree(job_id, sd, cfg, form), form))
+
+
+def work_unit(u: WorkUnit, form: str = "array") -> bytes:
+    return dumps(variant("WorkUnit", work_unit_tree(u), form))
 
 
 def done() -> bytes:
@@ -264,9 +293,9 @@ def worker_info(num_threads: int) -> bytes:
 
 def rows_ready_from_tree(ev) -> WorkUnitResult:
     """RenderEvent::RowsReady({work_unit, rows: [[{r,g,b}]]}) -> WorkUnitResult with rows [n][W][3] f64."""
-    if not (isinstance(ev, dict) and len(ev) == 1 and "RowsReady" in ev):
+    name, r = variant_parts(ev)
+    if name != "RowsReady" or r is None:
         raise CborError(f"expected RenderEvent::RowsReady, got {str(ev)[:80]}")
-    r = ev["RowsReady"]
     wu = r["work_unit"]
     rows = np.array([[[c["r"], c["g"], c["b"]] for c in row] for row in r["rows"]], dtype=np.float64)
     return WorkUnitResult(WorkUnit(wu["row_start"], wu["row_end"], tuple(wu["job_id"])), rows)
@@ -279,7 +308,8 @@ class NetworkWorker:
     """workers.rs:118-245: connect, read the node's WorkerInfo, then per job SetJob, two units in flight, one
     RenderEvent per unit, Done.  A node ends the connection after Done, so one NetworkWorker serves one job."""
 
-    def __init__(self, endpoint: str, timeout: Optional[float] = 600.0):
+    def __init__(self, endpoint: str, timeout: Optional[float] = 600.0, form: str = "array"):
+        self.form = form
         host, _, port = endpoint.rpartition(":") if ":" in endpoint else (endpoint, "", "")
         self.sock = socket.create_connection((host, int(port) if port else DEFAULT_PORT), timeout=timeout)
         self.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
@@ -302,7 +332,7 @@ class NetworkWorker:
         if units is None:
             units = [WorkUnit(u.row_start, u.row_end, tuple(job_id)) for u in work_units(h, cfg.rows_per_work_unit)]
         img = np.zeros((h, w, 3), np.float64)
-        self.sock.sendall(set_job(job_id, sd, cfg))
+        self.sock.sendall(set_job(job_id, sd, cfg, self.form))
 
         def collect():
             res = rows_ready_from_tree(load(self._read))
@@ -312,9 +342,9 @@ class NetworkWorker:
 
         sent = received = 0
         while sent < len(units) and sent < 2:
-            self.sock.sendall(work_unit(units[sent])); sent += 1
+            self.sock.sendall(work_unit(units[sent], self.form)); sent += 1
         while sent < len(units):
-            self.sock.sendall(work_unit(units[sent])); sent += 1
+            self.sock.sendall(work_unit(units[sent], self.form)); sent += 1
             collect(); received += 1
         while received < len(units):
             collect(); received += 1

@@ -105,6 +105,7 @@ void Reader::item(uint8_t first, Node &out, int depth) {
     if (depth > MAX_DEPTH) throw Error("cbor: nesting too deep");
     if (budget_-- == 0) throw Error("cbor: document too large");
     const uint8_t major = first >> 5, info = first & 31;
+    out.cbor = true;
     switch (major) {
     case 0:
         out.kind = Node::Scalar;

@@ -6,7 +6,10 @@
 // the same detail::Node tree the YAML reader builds, so that one scene_from_node() serves both formats.
 // Writer: the forms serde_cbor's default (non-packed) serializer chooses — structs as maps with text keys in
 // declaration order, sequences and tuples as definite-length arrays, unsigned integers in the shortest form,
-// f64 as f32 when that is exact (f16 for NaN and the infinities), otherwise f64.
+// f64 as f32 when that is exact (f16 for NaN and the infinities), otherwise f64.  Enums: a unit variant is its
+// name as text; a newtype variant is the 2-array [name, content] in serde_cbor < 0.10 (the reference pins 0.9.0;
+// later releases call it "legacy") and the one-entry map {name: content} from 0.10 on — the writer does either
+// (Writer::legacy_enums), the reader takes both.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -55,6 +58,13 @@ class Reader {
 class Writer {
   public:
     std::string out;
+    bool legacy_enums = true;   // [name, content] (serde_cbor < 0.10) instead of {name: content}
+    // the head of a newtype variant; its content follows
+    void variant(const char *name) {
+        if (legacy_enums) array(2);
+        else map(1);
+        text(name);
+    }
     void uint(uint64_t v) { head(0, v); }
     void array(uint64_t n) { head(4, n); }
     void map(uint64_t n) { head(5, n); }

@@ -337,11 +337,17 @@ Vec3 as_vec3(const Node &n, const std::string &what) {
     return Vec3{as_f64(n.seq[0], what), as_f64(n.seq[1], what), as_f64(n.seq[2], what)};
 }
 
-// externally tagged enum: a single-key map { Variant: {...} }
-const std::pair<std::string, Node> &variant_of(const Node &n, const char *what) {
-    if (n.kind != Node::Map || n.map.size() != 1)
-        throw Error(std::string(what) + ": expected a single-key map (externally tagged enum)");
-    return n.map[0];
+// externally tagged enum: a single-key map { Variant: {...} }; from CBOR also serde_cbor's array form
+// [ "Variant", {...} ] (the only form serde_cbor < 0.10 writes; the reference pins 0.9.0)
+struct VariantRef {
+    const std::string &first;
+    const Node &second;
+};
+VariantRef variant_of(const Node &n, const char *what) {
+    if (n.kind == Node::Map && n.map.size() == 1) return VariantRef{n.map[0].first, n.map[0].second};
+    if (n.cbor && n.kind == Node::Seq && n.seq.size() == 2 && n.seq[0].kind == Node::Scalar && n.seq[0].bin == Node::Text)
+        return VariantRef{n.seq[0].scalar, n.seq[1]};
+    throw Error(std::string(what) + ": expected a single-key map (externally tagged enum)");
 }
 
 MaterialData material_from_yaml(const Node &n) {

@@ -8,6 +8,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
 #include <condition_variable>
 #include <cstdio>
@@ -43,9 +44,8 @@ void put_color(Writer &w, const Vec3 &c) {   // color.rs:12-16
 }
 
 void put_material(Writer &w, const MaterialData &m) {   // shapes.rs:42-82, externally tagged
-    w.map(1);
     if (auto *x = std::get_if<MatteData>(&m)) {
-        w.text("Matte");
+        w.variant("Matte");
         w.map(3);
         w.key("diffuse_color");
         put_color(w, x->diffuse_color);
@@ -53,20 +53,20 @@ void put_material(Writer &w, const MaterialData &m) {   // shapes.rs:42-82, exte
         put_color(w, x->ambient_color);
         w.key("diffuse_coefficient").f64(x->diffuse_coefficient);
     } else if (auto *e = std::get_if<EmissiveData>(&m)) {
-        w.text("Emissive");
+        w.variant("Emissive");
         w.map(2);
         w.key("color");
         put_color(w, e->color);
         w.key("power").f64(e->power);
     } else if (auto *r = std::get_if<ReflectiveData>(&m)) {
-        w.text("Reflective");
+        w.variant("Reflective");
         w.map(2);
         w.key("reflect_amount").f64(r->reflect_amount);
         w.key("reflect_color");
         put_color(w, r->reflect_color);
     } else {
         const auto &g = std::get<GlossyReflectiveData>(m);
-        w.text("GlossyReflective");
+        w.variant("GlossyReflective");
         w.map(3);
         w.key("reflect_amount").f64(g.reflect_amount);
         w.key("reflect_color");
@@ -76,9 +76,8 @@ void put_material(Writer &w, const MaterialData &m) {   // shapes.rs:42-82, exte
 }
 
 void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:18-37 (+ extensions)
-    w.map(1);
     if (auto *sp = std::get_if<SphereData>(&s)) {
-        w.text("Sphere");
+        w.variant("Sphere");
         w.map(4);
         w.key("center");
         put_vec3(w, sp->center);
@@ -87,7 +86,7 @@ void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:1
         put_material(w, sp->material);
         w.key("invert").boolean(sp->invert);
     } else if (auto *pl = std::get_if<PlaneData>(&s)) {
-        w.text("Plane");
+        w.variant("Plane");
         w.map(3);
         w.key("point");
         put_vec3(w, pl->point);
@@ -96,7 +95,7 @@ void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:1
         w.key("material");
         put_material(w, pl->material);
     } else if (auto *t = std::get_if<TriangleData>(&s)) {
-        w.text("Triangle");
+        w.variant("Triangle");
         w.map(4);
         w.key("v0");
         put_vec3(w, t->v0);
@@ -107,7 +106,7 @@ void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:1
         w.key("material");
         put_material(w, t->material);
     } else if (auto *m = std::get_if<MeshData>(&s)) {
-        w.text("Mesh");
+        w.variant("Mesh");
         w.map(3);
         w.key("vertices").array(m->vertices.size());
         for (const Vec3 &v : m->vertices) put_vec3(w, v);
@@ -119,7 +118,7 @@ void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:1
         w.key("material");
         put_material(w, m->material);
     } else if (auto *r = std::get_if<RectangleData>(&s)) {
-        w.text("Rectangle");
+        w.variant("Rectangle");
         w.map(4);
         w.key("corner");
         put_vec3(w, r->corner);
@@ -131,7 +130,7 @@ void put_shape(Writer &w, const ShapeData &s) {   // scene.rs:71-74, shapes.rs:1
         put_material(w, r->material);
     } else {
         const auto &b = std::get<BoxData>(s);
-        w.text("Box");
+        w.variant("Box");
         w.map(3);
         w.key("min");
         put_vec3(w, b.min);
@@ -244,8 +243,9 @@ Job job_from(const Node &n) {
 }
 
 // an enum value: "Variant" (unit), {"Variant": content} (serde_cbor >= 0.9), or the older ["Variant", content]
-void variant_of(const Node &n, const char *what, std::string &tag, const Node *&content) {
+void variant_of(const Node &n, const char *what, std::string &tag, const Node *&content, EnumForm *form = nullptr) {
     content = nullptr;
+    if (form) *form = n.kind == Node::Map ? EnumForm::Map : EnumForm::Array;
     if (n.kind == Node::Scalar && n.bin == Node::Text) {
         tag = n.scalar;
     } else if (n.kind == Node::Map && n.map.size() == 1) {
@@ -262,8 +262,8 @@ void variant_of(const Node &n, const char *what, std::string &tag, const Node *&
 Request request_from(const Node &n) {
     std::string tag;
     const Node *content;
-    variant_of(n, "NetworkWorkerRequest", tag, content);
     Request r;
+    variant_of(n, "NetworkWorkerRequest", tag, content, &r.form);
     if (tag == "Done") {
         r.kind = Request::Done;
     } else if (tag == "WorkUnit") {
@@ -362,10 +362,10 @@ std::string encode_worker_info(uint64_t num_threads) {
     return w.out;
 }
 
-std::string encode_set_job(const Job &job) {
+std::string encode_set_job(const Job &job, EnumForm form) {
     Writer w;
-    w.map(1);
-    w.text("SetJob");
+    w.legacy_enums = form == EnumForm::Array;
+    w.variant("SetJob");
     w.map(3);
     w.key("id");
     put_job_id(w, job.id.allocator_id, job.id.id);
@@ -378,10 +378,10 @@ std::string encode_set_job(const Job &job) {
     return w.out;
 }
 
-std::string encode_work_unit(const WorkUnit &unit) {
+std::string encode_work_unit(const WorkUnit &unit, EnumForm form) {
     Writer w;
-    w.map(1);
-    w.text("WorkUnit");
+    w.legacy_enums = form == EnumForm::Array;
+    w.variant("WorkUnit");
     put_work_unit(w, unit);
     return w.out;
 }
@@ -392,14 +392,14 @@ std::string encode_done() {
     return w.out;
 }
 
-std::string encode_rows_ready(const WorkUnitResult &r, uint32_t width) {
+std::string encode_rows_ready(const WorkUnitResult &r, uint32_t width, EnumForm form) {
     const size_t row_elems = (size_t)width * 3;
     if (row_elems == 0 || r.rows.size() % row_elems) throw Error("encode_rows_ready: rows do not match the width");
     const size_t n_rows = r.rows.size() / row_elems;
     Writer w;
     w.out.reserve(64 + r.rows.size() * 10);
-    w.map(1);
-    w.text("RowsReady");
+    w.legacy_enums = form == EnumForm::Array;
+    w.variant("RowsReady");
     w.map(2);
     w.key("work_unit");
     put_work_unit(w, r.work_unit);
@@ -507,6 +507,7 @@ void NodeServer::handle_client(int fd, const std::string &peer) {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::pair<WorkUnitResult, uint32_t>> queue;
+    std::atomic<EnumForm> form{EnumForm::Array};   // answer in the form the manager writes (serde_cbor < 0.10 reads no other)
     bool closing = false;
     std::string send_error;
     std::thread sender([&] {
@@ -518,7 +519,7 @@ void NodeServer::handle_client(int fd, const std::string &peer) {
             queue.pop_front();
             lk.unlock();
             try {
-                send_all(fd, encode_rows_ready(item.first, item.second));
+                send_all(fd, encode_rows_ready(item.first, item.second, form.load()));
             } catch (const std::exception &e) {
                 std::lock_guard<std::mutex> g(mu);
                 send_error = e.what();   // "Manager connection error" in the reference: stop sending
@@ -541,6 +542,7 @@ void NodeServer::handle_client(int fd, const std::string &peer) {
         Node node;
         while (reader.next(node)) {
             Request req = request_from(node);
+            if (req.kind != Request::Done) form.store(req.form);
             if (req.kind == Request::SetJob) {
                 std::printf("Got job\n");
                 std::fflush(stdout);
@@ -571,7 +573,7 @@ void NodeServer::handle_client(int fd, const std::string &peer) {
 // ------------------------------------------------------------------------------------------------
 // NetworkWorker
 // ------------------------------------------------------------------------------------------------
-NetworkWorker::NetworkWorker(const std::string &raw_endpoint) {
+NetworkWorker::NetworkWorker(const std::string &raw_endpoint, EnumForm form) : form_(form) {
     // workers.rs:119-123: "host" gets the default port
     const size_t colon = raw_endpoint.rfind(':');
     const std::string host = colon == std::string::npos ? raw_endpoint : raw_endpoint.substr(0, colon);
@@ -615,7 +617,7 @@ Image NetworkWorker::render_job(const Job &job) {
     Image img(W, H);
     std::vector<WorkUnit> units = work_units(H, job.config.rows_per_work_unit, job.id.id);
     for (WorkUnit &u : units) u.job_allocator_id = job.id.allocator_id;
-    send_all(fd_, encode_set_job(job));
+    send_all(fd_, encode_set_job(job, form_));
     auto collect = [&] {
         if (!reader.next(node)) throw Error("network node closed the connection before all results arrived");
         uint32_t w = 0;
@@ -627,9 +629,9 @@ Image NetworkWorker::render_job(const Job &job) {
     };
     // two units in flight (workers.rs:160-175), then one result per further unit, then the tail
     size_t sent = 0, received = 0;
-    for (; sent < units.size() && sent < 2; sent++) send_all(fd_, encode_work_unit(units[sent]));
+    for (; sent < units.size() && sent < 2; sent++) send_all(fd_, encode_work_unit(units[sent], form_));
     for (; sent < units.size(); sent++) {
-        send_all(fd_, encode_work_unit(units[sent]));
+        send_all(fd_, encode_work_unit(units[sent], form_));
         collect();
         received++;
     }

@@ -15,6 +15,8 @@
 //
 // The Rust reference cannot be built in this image, so the wire forms follow serde_cbor's documented behaviour
 // and are pinned only by hand-derived byte vectors (tests/test_net_protocol.py), not by the reference itself.
+// The one point on which serde_cbor releases differ — the form of enum variants — is handled without a guess:
+// the node answers in the form the manager's requests arrive in, and the manager's end defaults to the 0.9 form.
 #pragma once
 #include <atomic>
 #include <cstdint>
@@ -32,18 +34,23 @@ namespace net {
 
 constexpr const char *DEFAULT_PORT = "2000";   // constants.rs:6
 
+// How a newtype enum variant travels: serde_cbor < 0.10 (the reference pins 0.9.0) writes the 2-array
+// [name, content]; 0.10 and later write the one-entry map {name: content} and read both.
+enum class EnumForm { Array, Map };
+
 struct Request {   // NetworkWorkerRequest, workers.rs:106-110
     enum Kind { SetJob, Unit, Done } kind = Done;
+    EnumForm form = EnumForm::Array;   // the form this request arrived in (a unit variant has none: Array)
     Job job;
     WorkUnit unit{0, 0, 0, 0};
 };
 
 // ---- wire forms (pure functions; tests call them through `fluxb200-node --encode/--decode`) ----
 std::string encode_worker_info(uint64_t num_threads);                        // manager.rs:221-224
-std::string encode_set_job(const Job &job);
-std::string encode_work_unit(const WorkUnit &unit);
+std::string encode_set_job(const Job &job, EnumForm form = EnumForm::Array);
+std::string encode_work_unit(const WorkUnit &unit, EnumForm form = EnumForm::Array);
 std::string encode_done();
-std::string encode_rows_ready(const WorkUnitResult &r, uint32_t width);     // RenderEvent::RowsReady
+std::string encode_rows_ready(const WorkUnitResult &r, uint32_t width, EnumForm form = EnumForm::Array);   // RenderEvent::RowsReady
 // one item from the front of `data`; `used` = its length.  Throw flux::Error on malformed input.
 Request decode_request(const void *data, size_t n, size_t *used = nullptr);
 uint64_t decode_worker_info(const void *data, size_t n, size_t *used = nullptr);
@@ -72,7 +79,7 @@ class NodeServer {
 // ---- the manager's end (workers.rs:118-245) ----
 class NetworkWorker {
   public:
-    explicit NetworkWorker(const std::string &endpoint);   // "host" or "host:port"
+    explicit NetworkWorker(const std::string &endpoint, EnumForm form = EnumForm::Array);   // "host" or "host:port"
     ~NetworkWorker();
     NetworkWorker(const NetworkWorker &) = delete;
     NetworkWorker &operator=(const NetworkWorker &) = delete;
@@ -85,6 +92,7 @@ class NetworkWorker {
     int fd_ = -1;
     WorkerInfo info_;
     std::string endpoint_;
+    EnumForm form_;
 };
 
 }  // namespace net

@@ -25,6 +25,7 @@ struct Config {   // flux/src/main.rs:114-124
     uint32_t gpus = 1, width = 0, height = 0;
     uint64_t seed = 1;
     std::vector<int> devices;
+    bool enum_map = false;
 };
 
 [[noreturn]] void usage(const char *msg) {
@@ -38,6 +39,7 @@ struct Config {   // flux/src/main.rs:114-124
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
                  "        --devices <LIST>   Explicit CUDA device list instead of -G, e.g. 0,2,3\n"
                  "    -n, --node <ADDRESS[:PORT]>   Render using the fluxb200-node / flux-node process at this address\n"
+                 "        --enum-form <array|map>   With -n: CBOR form of enum variants, serde_cbor < 0.10 (default) or >= 0.10\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
                  "        --width <W> --height <H>   Override the scene's image size\n"
                  "    -o <FILE>              Output file [default: <scene_name>.ppm]\n"
@@ -66,6 +68,11 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
         else if (a == "-n" || a == "--node") c.node = next("--node");
+        else if (a == "--enum-form") {   // with -n: how enum variants are written (see host/fluxnet.hpp)
+            const std::string f = next("--enum-form");
+            if (f != "array" && f != "map") usage("--enum-form takes array or map");
+            c.enum_map = f == "map";
+        }
         else if (a == "--devices") {   // explicit device list, e.g. 0,0 = two contexts on one GPU (tests of the sharded path)
             for (const char *p = next("--devices"); *p;) {
                 char *end = nullptr;
@@ -106,7 +113,7 @@ int main(int argc, char **argv) {
         netcfg.max_trace_depth = config.max_depth;
         netcfg.rows_per_work_unit = config.rows_per_work_unit;
         if (!config.node.empty()) {
-            flux::net::NetworkWorker node(config.node);
+            flux::net::NetworkWorker node(config.node, config.enum_map ? flux::net::EnumForm::Map : flux::net::EnumForm::Array);
             std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),
                         netcfg.sample_root * netcfg.sample_root, netcfg.sample_root == 1 ? "" : "s", netcfg.max_trace_depth);
             flux::Image img = node.render_job(flux::Job{flux::JobID{config.seed, 0}, s, netcfg});

@@ -16,6 +16,7 @@ struct Node {
     enum Bin { Text, F64, U64, I64, Bool } bin = Text;
     std::string scalar;
     bool quoted = false;   // text that must not be read as a number / boolean
+    bool cbor = false;     // built by the CBOR reader: enums may come in serde_cbor's array form [variant, content]
     double f = 0.0;
     uint64_t u = 0;        // U64 value, I64 two's complement, Bool 0/1
     std::vector<Node> seq;

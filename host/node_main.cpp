@@ -13,6 +13,7 @@
 //   --decode-flat FILE OUT   decode the SetJob at the front of FILE and write its flattened scene to OUT
 //   --reencode FILE      decode the requests in FILE and write them again to stdout
 //   --rows-ready ROW_START ROW_END WIDTH ALLOC_ID JOB_ID   read raw f64 RGB from stdin, write RenderEvent::RowsReady
+//   --enum-form array|map   (before --rows-ready) the enum form to write: serde_cbor < 0.10 (default) or >= 0.10
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,8 +63,8 @@ int codec_requests(const std::string &path, bool reencode) {
         const flux::net::Request r = flux::net::decode_request(data.data() + off, data.size() - off, &used);
         off += used;
         if (reencode) {
-            const std::string out = r.kind == flux::net::Request::SetJob ? flux::net::encode_set_job(r.job)
-                                    : r.kind == flux::net::Request::Unit ? flux::net::encode_work_unit(r.unit)
+            const std::string out = r.kind == flux::net::Request::SetJob ? flux::net::encode_set_job(r.job, r.form)
+                                    : r.kind == flux::net::Request::Unit ? flux::net::encode_work_unit(r.unit, r.form)
                                                                          : flux::net::encode_done();
             std::fwrite(out.data(), 1, out.size(), stdout);
         } else if (r.kind == flux::net::Request::SetJob) {
@@ -86,6 +87,8 @@ int codec_requests(const std::string &path, bool reencode) {
     return 0;
 }
 
+flux::net::EnumForm g_form = flux::net::EnumForm::Array;
+
 int codec_rows_ready(char **v) {
     flux::WorkUnit u{(uint32_t)parse_u64(v[0], "ROW_START"), (uint32_t)parse_u64(v[1], "ROW_END"), parse_u64(v[4], "JOB_ID"),
                      parse_u64(v[3], "ALLOC_ID")};
@@ -94,7 +97,7 @@ int codec_rows_ready(char **v) {
     if (raw.size() % sizeof(double)) throw flux::Error("stdin is not a whole number of doubles");
     flux::WorkUnitResult r{u, std::vector<double>(raw.size() / sizeof(double))};
     std::memcpy(r.rows.data(), raw.data(), raw.size());
-    const std::string out = flux::net::encode_rows_ready(r, width);
+    const std::string out = flux::net::encode_rows_ready(r, width, g_form);
     std::fwrite(out.data(), 1, out.size(), stdout);
     return 0;
 }
@@ -126,6 +129,11 @@ int main(int argc, char **argv) {
                 }
             } else if (a == "--seed") seed = parse_u64(next("--seed"), "--seed");
             else if (a == "--clients") clients = parse_u64(next("--clients"), "--clients");
+            else if (a == "--enum-form") {   // codec tools only: the server mirrors its client
+                const std::string f = next("--enum-form");
+                if (f != "array" && f != "map") usage("--enum-form takes array or map");
+                g_form = f == "map" ? flux::net::EnumForm::Map : flux::net::EnumForm::Array;
+            }
             else if (a == "--decode") return codec_requests(next("--decode"), false);
             else if (a == "--reencode") return codec_requests(next("--reencode"), true);
             else if (a == "--decode-flat") {

@@ -26,14 +26,28 @@ def start_node(*extra):
     return p, int(line.rsplit(":", 1)[1])
 
 
-def test_python_manager_gets_the_rows_the_gpu_renders(gpu_ctx):
+@pytest.mark.parametrize("form", ["array", "map"])
+def test_python_manager_gets_the_rows_the_gpu_renders(gpu_ctx, form):
+    """The node answers in the enum form its manager writes (serde_cbor < 0.10 reads only the array form)."""
     sd = Hp.deterministic_scene(96, 64)
     cfg = JobConfiguration(4, 5, 10)
     proc, port = start_node("--seed", "5")
     try:
-        w = N.NetworkWorker(f"127.0.0.1:{port}", timeout=120)
+        w = N.NetworkWorker(f"127.0.0.1:{port}", timeout=120, form=form)
         assert w.info() == {"num_threads": 1}
-        img = w.render_job(sd, cfg, job_id=(2 ** 64 - 1, 9))
+        seen = []
+        raw_load = N.load
+        def spy(read, _depth=0):   # what arrives, before NetworkWorker interprets it
+            v = raw_load(read, _depth)
+            if _depth == 0:
+                seen.append(type(v))
+            return v
+        N.load = spy
+        try:
+            img = w.render_job(sd, cfg, job_id=(2 ** 64 - 1, 9))
+        finally:
+            N.load = raw_load
+        assert set(seen) == {list if form == "array" else dict}
         assert proc.wait(30) == 0
     finally:
         if proc.poll() is None:

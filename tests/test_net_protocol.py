@@ -4,7 +4,9 @@ RenderEvent::RowsReady (fluxcore/src/workers.rs:106-110, manager.rs:16-28,221-22
 Two implementations written independently — C++ (host/cbor.cpp, host/fluxnet.cpp, driven through the codec tools of
 `fluxb200-node`) and Python (flux_b200/netproto.py) — against each other and against byte vectors derived by hand
 from RFC 7049.  No GPU: nothing here renders.  The Rust reference cannot be built in this image, so
-these vectors pin the documented serde_cbor forms, not the reference binary."""
+these vectors pin the documented serde_cbor forms, not the reference binary.  Enum variants are exercised in both of
+serde_cbor's forms: the 2-array of releases < 0.10 (the reference pins 0.9.0; the default here) and the one-entry map
+of later releases."""
 import os
 import struct
 import subprocess
@@ -38,16 +40,21 @@ def run(node, *args, stdin=None, ok=True):
 # ---- hand-derived vectors (RFC 7049 §2.1: major type << 5 | length; text = 0x60+len; map = 0xa0+n; array = 0x80+n)
 WORKER_INFO_8 = bytes.fromhex("a1" "6b") + b"num_threads" + bytes.fromhex("08")
 DONE = bytes.fromhex("64") + b"Done"
-WORK_UNIT = (bytes.fromhex("a1" "68") + b"WorkUnit" + bytes.fromhex("a3")
-             + bytes.fromhex("69") + b"row_start" + bytes.fromhex("00")
-             + bytes.fromhex("67") + b"row_end" + bytes.fromhex("1831")                 # 49 -> 0x18 0x31
-             + bytes.fromhex("66") + b"job_id" + bytes.fromhex("82" "1b" "0123456789abcdef" "19" "0100"))   # (u64, 256)
+_WORK_UNIT_BODY = (bytes.fromhex("a3")
+                   + bytes.fromhex("69") + b"row_start" + bytes.fromhex("00")
+                   + bytes.fromhex("67") + b"row_end" + bytes.fromhex("1831")                 # 49 -> 0x18 0x31
+                   + bytes.fromhex("66") + b"job_id" + bytes.fromhex("82" "1b" "0123456789abcdef" "19" "0100"))   # (u64, 256)
+# NetworkWorkerRequest::WorkUnit(..): the 2-array [name, content] of serde_cbor < 0.10 (the reference pins 0.9.0) ...
+WORK_UNIT = bytes.fromhex("82" "68") + b"WorkUnit" + _WORK_UNIT_BODY
+# ... and the one-entry map {name: content} of serde_cbor >= 0.10
+WORK_UNIT_MAP = bytes.fromhex("a1" "68") + b"WorkUnit" + _WORK_UNIT_BODY
 
 
 def test_python_codec_matches_hand_derived_vectors():
     assert N.worker_info(8) == WORKER_INFO_8
     assert N.done() == DONE
     assert N.work_unit(WorkUnit(0, 49, (0x0123456789ABCDEF, 256))) == WORK_UNIT
+    assert N.work_unit(WorkUnit(0, 49, (0x0123456789ABCDEF, 256)), "map") == WORK_UNIT_MAP
     # RFC 7049 appendix A examples
     assert N.dumps(1000000) == bytes.fromhex("1a000f4240")
     assert N.dumps(1.5) == bytes.fromhex("fa3fc00000")             # serde_cbor narrows to f32, not to f16
@@ -66,10 +73,11 @@ def test_python_codec_matches_hand_derived_vectors():
 
 def test_cpp_decodes_hand_derived_requests(node, tmp_path):
     f = tmp_path / "reqs.cbor"
-    f.write_bytes(WORK_UNIT + DONE)
+    f.write_bytes(WORK_UNIT + WORK_UNIT_MAP + DONE)
     out = run(node, "--decode", str(f)).stdout.decode().splitlines()
-    assert out == [f"WorkUnit rows=0..49 job=({0x0123456789ABCDEF},256)", "Done"]
-    assert run(node, "--reencode", str(f)).stdout == WORK_UNIT + DONE   # shortest-form integers, same key order
+    assert out == [f"WorkUnit rows=0..49 job=({0x0123456789ABCDEF},256)"] * 2 + ["Done"]
+    # shortest-form integers, same key order, each request in the enum form it arrived in
+    assert run(node, "--reencode", str(f)).stdout == WORK_UNIT + WORK_UNIT_MAP + DONE
 
 
 def _scenes():
@@ -81,14 +89,16 @@ def _scenes():
     yield "glossy", synth.glossy_scene()                                    # all four material kinds
 
 
+@pytest.mark.parametrize("form", ["array", "map"])
 @pytest.mark.parametrize("name,sd", list(_scenes()), ids=[n for n, _ in _scenes()])
-def test_set_job_round_trip_between_the_two_codecs(node, tmp_path, name, sd):
+def test_set_job_round_trip_between_the_two_codecs(node, tmp_path, name, sd, form):
     """Python encodes SetJob; C++ decodes it into the same flattened scene the Python host hands the C-ABI, and
     encodes it again to the very same bytes."""
     cfg = JobConfiguration(7, 4, 13)
-    msg = N.set_job((2 ** 63 + 5, 3), sd, cfg)
+    msg = N.set_job((2 ** 63 + 5, 3), sd, cfg, form)
+    assert msg[:1] == (b"\x82" if form == "array" else b"\xa1") and msg[1:8] == b"\x66SetJob"
     f = tmp_path / "job.cbor"
-    f.write_bytes(msg + N.work_unit(WorkUnit(13, 25, (2 ** 63 + 5, 3))) + N.done())
+    f.write_bytes(msg + N.work_unit(WorkUnit(13, 25, (2 ** 63 + 5, 3)), form) + N.done())
     lines = run(node, "--decode", str(f)).stdout.decode().splitlines()
     assert len(lines) == 3 and lines[2] == "Done"
     assert lines[0].startswith(f"SetJob id=({2 ** 63 + 5},3) scene={sd.scene_name} "
@@ -105,7 +115,7 @@ def test_decoder_accepts_every_form_serde_would(node, tmp_path):
     """Indefinite-length containers, f16 / f64 floats where f32 would do, integers for f64 fields, unknown keys,
     Color as a sequence, structs as sequences, the older array form of enums, tags."""
     sd = Hp.deterministic_scene(40, 30)
-    tree = {"id": [1, 2], "scene_data": N.scene_tree(sd), "config": {"sample_root": 2, "max_trace_depth": 5, "rows_per_work_unit": 50}}
+    tree = {"id": [1, 2], "scene_data": N.scene_tree(sd, "map"), "config": {"sample_root": 2, "max_trace_depth": 5, "rows_per_work_unit": 50}}
     tree["scene_data"]["background"] = [0, 0, 0]                       # Color via visit_seq, integers for f64
     tree["scene_data"]["extra_key_from_a_newer_manager"] = {"x": [1, 2, 3]}
     tree["config"] = [2, 5, 50]                                        # struct via visit_seq
@@ -122,7 +132,7 @@ def test_decoder_accepts_every_form_serde_would(node, tmp_path):
             return b"\x7f" + N.dumps(x[:2]) + N.dumps(x[2:]) + b"\xff"
         return N.dumps(x)
 
-    legacy = b"\x82" + N.dumps("SetJob") + b"\xc1" + indefinite(tree)    # ["SetJob", tag(1) content]
+    legacy = b"\x82" + N.dumps("SetJob") + b"\xc1" + indefinite(tree)    # ["SetJob", tag(1) content], map-form enums inside
     f1, f2 = tmp_path / "a.cbor", tmp_path / "b.cbor"
     f1.write_bytes(canonical)
     f2.write_bytes(legacy + b"\x82" + N.dumps("WorkUnit") + N.dumps(N.work_unit_tree(WorkUnit(1, 2, (3, 4)))) + b"\x81" + N.dumps("Done"))
@@ -149,7 +159,7 @@ def test_decoder_accepts_every_form_serde_would(node, tmp_path):
 ])
 def test_malformed_jobs_are_rejected_with_serde_style_messages(node, tmp_path, mutate, message):
     sd = Hp.deterministic_scene(40, 30)
-    tree = {"id": [1, 2], "scene_data": N.scene_tree(sd), "config": {"sample_root": 2, "max_trace_depth": 5, "rows_per_work_unit": 50}}
+    tree = {"id": [1, 2], "scene_data": N.scene_tree(sd, "map"), "config": {"sample_root": 2, "max_trace_depth": 5, "rows_per_work_unit": 50}}
     mutate(tree)
     f = tmp_path / "bad.cbor"
     f.write_bytes(N.dumps({"SetJob": tree}))
@@ -192,10 +202,13 @@ def test_rows_ready_encoding_is_exact_for_every_kind_of_double(node):
                float(np.float32(0.1)), 1.401298464324817e-45, 3.4028234663852886e+38]
     px[12:15] = [3.4028234663852886e+38 * 2, 1e308, 1 + 2 ** -52]
     out = run(node, "--rows-ready", "10", "13", str(width), str(2 ** 64 - 1), "5", stdin=px.tobytes()).stdout
+    as_map = run(node, "--enum-form", "map", "--rows-ready", "10", "13", str(width), str(2 ** 64 - 1), "5", stdin=px.tobytes()).stdout
+    assert out[:11] == b"\x82\x69RowsReady" and as_map[:11] == b"\xa1\x69RowsReady" and out[1:] == as_map[1:]
     tree, used = N.loads(out)
     assert used == len(out)
-    assert list(tree) == ["RowsReady"] and list(tree["RowsReady"]) == ["work_unit", "rows"]
-    assert list(tree["RowsReady"]["rows"][0][0]) == ["r", "g", "b"]
+    assert tree[0] == "RowsReady" and list(tree[1]) == ["work_unit", "rows"]
+    assert list(tree[1]["rows"][0][0]) == ["r", "g", "b"]
+    assert N.rows_ready_from_tree(N.loads(as_map)[0]).rows.tobytes() == N.rows_ready_from_tree(tree).rows.tobytes()
     res = N.rows_ready_from_tree(tree)
     assert (res.work_unit.row_start, res.work_unit.row_end, res.work_unit.job_id) == (10, 13, (2 ** 64 - 1, 5))
     got = res.rows.ravel()
@@ -205,8 +218,8 @@ def test_rows_ready_encoding_is_exact_for_every_kind_of_double(node):
     head = out.index(b"\xa3\x61r")
     assert out[head:head + 22] == bytes.fromhex("a3" "6172" "fa00000000" "6167" "fa80000000" "6162" "fa3f800000")
     # and the Python encoder agrees with the C++ one on the whole message
-    again = N.dumps({"RowsReady": {"work_unit": N.work_unit_tree(res.work_unit),
-                                   "rows": [[N._color(c) for c in row] for row in px.reshape(n_rows, width, 3)]}})
+    again = N.dumps(["RowsReady", {"work_unit": N.work_unit_tree(res.work_unit),
+                                   "rows": [[N._color(c) for c in row] for row in px.reshape(n_rows, width, 3)]}])
     assert again == out
     # rows that do not match the width are refused
     p = run(node, "--rows-ready", "0", "0", "7", "0", "0", stdin=px.tobytes(), ok=False)
@@ -233,7 +246,7 @@ class FakeNode:
         self.srv = socket.create_server(("127.0.0.1", 0))
         self.port = self.srv.getsockname()[1]
         self.num_threads = num_threads
-        self.events, self.error = [], None
+        self.events, self.error, self.forms = [], None, set()
         self.thread = threading.Thread(target=self._serve, daemon=True)
         self.thread.start()
 
@@ -259,20 +272,23 @@ class FakeNode:
                 if req == "Done":
                     self.events.append("Done")
                     break
-                (tag, body), = req.items()
+                tag, body = N.variant_parts(req)
+                form = "map" if isinstance(req, dict) else "array"
+                self.forms.add(form)
                 if tag == "SetJob":
                     width = body["scene_data"]["output_settings"]["image_width"]
                     self.events.append(("SetJob", tuple(body["id"]), body["scene_data"]["scene_name"], body["config"]))
                 else:
                     self.events.append(("WorkUnit", body["row_start"], body["row_end"], tuple(body["job_id"])))
                     rows = [[dict(zip("rgb", self.colour(r, c))) for c in range(width)] for r in range(body["row_start"], body["row_end"] + 1)]
-                    conn.sendall(N.dumps({"RowsReady": {"work_unit": body, "rows": rows}}))
+                    conn.sendall(N.dumps(N.variant("RowsReady", {"work_unit": body, "rows": rows}, form)))
             conn.close()
         except Exception as e:   # surfaced by the test
             self.error = e
 
 
-def test_cpp_network_worker_drives_a_node(node, tmp_path):
+@pytest.mark.parametrize("form", ["array", "map"])
+def test_cpp_network_worker_drives_a_node(node, tmp_path, form):
     """`fluxb200 -n host:port` (NetworkWorker, workers.rs:118-245): reads WorkerInfo, sends SetJob, the work units of
     Job::work_units in order, Done; assembles the rows it gets back and writes the PPM."""
     import ctypes
@@ -280,12 +296,14 @@ def test_cpp_network_worker_drives_a_node(node, tmp_path):
     fake = FakeNode()
     out = tmp_path / "net.ppm"
     p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-n", f"127.0.0.1:{fake.port}",
-                        "-r", "3", "-d", "4", "-R", "7", "--width", "24", "--height", "20", "--seed", "99", "-o", str(out)],
+                        "-r", "3", "-d", "4", "-R", "7", "--width", "24", "--height", "20", "--seed", "99", "-o", str(out),
+                        "--enum-form", form],
                        capture_output=True, timeout=120)
     fake.thread.join(10)
     assert fake.error is None, fake.error
     assert p.returncode == 0, p.stderr.decode()
     assert b"Threads: 3" in p.stdout
+    assert fake.forms == {form}
     assert fake.events[0] == ("SetJob", (99, 0), "demo1", {"sample_root": 3, "max_trace_depth": 4, "rows_per_work_unit": 7})
     assert fake.events[1:-1] == [("WorkUnit", 0, 6, (99, 0)), ("WorkUnit", 7, 13, (99, 0)), ("WorkUnit", 14, 19, (99, 0))]
     assert fake.events[-1] == "Done"
@@ -295,10 +313,11 @@ def test_cpp_network_worker_drives_a_node(node, tmp_path):
     assert out.read_bytes() == ref.read_bytes()
 
 
-def test_python_network_worker_drives_a_node():
+@pytest.mark.parametrize("form", ["array", "map"])
+def test_python_network_worker_drives_a_node(form):
     fake = FakeNode(num_threads=5)
     sd = Hp.deterministic_scene(10, 9)
-    w = N.NetworkWorker(f"127.0.0.1:{fake.port}", timeout=30)
+    w = N.NetworkWorker(f"127.0.0.1:{fake.port}", timeout=30, form=form)
     assert w.info() == {"num_threads": 5}
     img = w.render_job(sd, JobConfiguration(2, 5, 4), job_id=(7, 1))
     fake.thread.join(10)
