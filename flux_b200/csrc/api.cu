@@ -779,7 +779,7 @@ int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const d
     CK(cudaEventRecord(ctx->ev1, us));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream);
+    launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaGetLastError());
@@ -805,7 +805,8 @@ int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d,
         CK(cudaMemcpyAsync(ctx->ray_o.p, o + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->ray_d.p, d + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        launch_trace_rays(ctx->scene, c, ctx->ray_o.p, ctx->ray_d.p, ctx->ray_hit.p, ctx->ray_t.p, ctx->sm_count, ctx->stream);
+        launch_trace_rays(ctx->scene, c, ctx->ray_o.p, ctx->ray_d.p, ctx->ray_hit.p, ctx->ray_t.p, ctx->sm_count, ctx->stream,
+                          ctx->count ? ctx->counters.p : nullptr);
         ctx->launches += 1;
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaGetLastError());

@@ -258,16 +258,21 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
 // rays; a lane whose ray is finished takes the chunk's next ray at once (ballot rank, no atomics), so the node loop
 // keeps running with (almost) all lanes instead of waiting for the warp's longest traversal — ncu on the
 // ray-per-thread form showed 6.9 of 32 lanes per instruction (profiles/r1s_bvh_kernels_full.txt).
+template <bool COUNT>
 __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n, uint32_t rays_per_warp,
                                                              const double *__restrict__ o, const double *__restrict__ d,
-                                                             int32_t *__restrict__ hit, double *__restrict__ t) {
+                                                             int32_t *__restrict__ hit, double *__restrict__ t,
+                                                             unsigned long long *__restrict__ counters) {
     extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x]
     uint2 *stack = bvh_stack + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint64_t next = warp_global * rays_per_warp;
     const uint64_t end = next + rays_per_warp < n ? next + rays_per_warp : n;
-    BvhTraversal<false> T;
+    BvhTraversal<COUNT> T;
+    unsigned long long cn[COUNT ? CN_COUNT : 1];
+    if (COUNT)
+        for (int k = 0; k < CN_COUNT; k++) cn[k] = 0;
     bool has = false;
     uint64_t mine = 0;
     for (;;) {
@@ -275,7 +280,8 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
         if (!has) {
             const uint64_t i = next + __popc(need & lt_mask);
             if (i < end) {
-                T.begin(sc, make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), nullptr);
+                if (COUNT) cn[CN_SEGMENTS]++;
+                T.begin(sc, make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), cn);
                 has = true;
                 mine = i;
             }
@@ -283,10 +289,11 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
         next += __popc(need);
         if (!__any_sync(0xffffffffu, has)) break;
         if (has) {
-            T.descend(sc, stack, blockDim.x, nullptr);
-            if (!T.done()) T.leaf(sc, stack, blockDim.x, nullptr);
+            T.descend(sc, stack, blockDim.x, cn);
+            if (!T.done()) T.leaf(sc, stack, blockDim.x, cn);
             if (T.done()) {
                 if (T.best.shape_id == 0xFFFFFFFFu) {
+                    if (COUNT) cn[CN_MISS]++;
                     hit[mine] = -1;
                     t[mine] = __longlong_as_double(0x7FF0000000000000ll);
                 } else {
@@ -297,10 +304,14 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
             }
         }
     }
+    if (COUNT) {
+        for (int k = 0; k < CN_COUNT; k++)
+            if (cn[k]) atomicAdd(counters + k, cn[k]);
+    }
 }
 
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
-                       int sm_count, cudaStream_t stream) {
+                       int sm_count, cudaStream_t stream, unsigned long long *counters) {
     if (n == 0) return;
     const int threads = 128;
     uint64_t want = (n + threads - 1) / threads;
@@ -311,7 +322,9 @@ void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const do
         const uint64_t warps = (n + rpw - 1) / rpw;
         const size_t smem = (size_t)BVH_STACK * threads * sizeof(uint2);
         const int blocks = (int)((warps * 32 + threads - 1) / threads);
-        trace_rays_bvh_kernel<<<blocks, threads, smem, stream>>>(sc, n, (uint32_t)rpw, o, d, hit, t);
+        // with counters (flux_enable_counters): segments = rays, nodes_visited, bbox / triangle tests, candidates, misses
+        if (counters) trace_rays_bvh_kernel<true><<<blocks, threads, smem, stream>>>(sc, n, (uint32_t)rpw, o, d, hit, t, counters);
+        else trace_rays_bvh_kernel<false><<<blocks, threads, smem, stream>>>(sc, n, (uint32_t)rpw, o, d, hit, t, nullptr);
     } else {
         uint64_t cap = (uint64_t)sm_count * 16;
         int blocks = (int)(want < cap ? want : cap);

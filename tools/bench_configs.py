@@ -43,6 +43,12 @@ def render_config(ctx, name, sd, root, depth=5, seed=1, reps=2):
            "ops_per_sample": algorithmic_ops(cn) / max(1, cn["samples"]),
            "nodes_per_segment": cn["nodes_visited"] / max(1, cn["segments"]),
            "prim_tests_per_segment": (cn["bbox_tests"] + cn["tri_tests"]) / max(1, cn["segments"])}
+    # SURVEY.md §8d for BVH configs: algorithmic bytes = nodes_visited * node_bytes + prims_tested * prim_bytes
+    # (128-byte nodes, 112-byte sphere records, 96-byte triangle records), set against the HBM peak
+    seg = max(1, cn["segments"])
+    bytes_per_segment = (cn["nodes_visited"] * 128 + cn["bbox_tests"] * 112 + cn["tri_tests"] * 96) / seg
+    out["alg_bytes_per_segment"] = bytes_per_segment
+    out["alg_GB_per_s"] = bytes_per_segment * out["segments_per_sample"] * n / (best * 1e-3) / 1e9
     print(json.dumps(out), flush=True)
     return out
 
@@ -58,8 +64,19 @@ def c5(ctx, n_total=100_000_000, chunk=10_000_000):
         ms_total += ctx.last_kernel_ms()
         hits += int((hit >= 0).sum())
         csum = (csum + int(hit.astype(np.int64).sum())) & 0xFFFFFFFFFFFF
+    # event counts on the first chunk (the instrumented instantiation is slower: not part of the timing)
+    o, d = synth.random_rays(chunk, seed=5, chunk_offset=0)
+    ctx.enable_counters(True)
+    ctx.reset_counters()
+    ctx.trace_rays(o, d)
+    cn = ctx.counters()
+    ctx.enable_counters(False)
+    bytes_per_ray = (cn["nodes_visited"] * 128 + cn["bbox_tests"] * 112) / max(1, cn["segments"])
     out = {"config": "c5 100M rays x 10K spheres (BVH)", "rays": n_total, "kernel_ms": ms_total,
-           "Mrays_per_s": n_total / (ms_total * 1e-3) / 1e6, "hit_fraction": hits / n_total, "hit_id_checksum": csum}
+           "Mrays_per_s": n_total / (ms_total * 1e-3) / 1e6, "hit_fraction": hits / n_total, "hit_id_checksum": csum,
+           "nodes_per_ray": cn["nodes_visited"] / max(1, cn["segments"]), "sphere_tests_per_ray": cn["bbox_tests"] / max(1, cn["segments"]),
+           "quadratics_per_ray": cn["bbox_pass"] / max(1, cn["segments"]), "alg_bytes_per_ray": bytes_per_ray,
+           "alg_GB_per_s": bytes_per_ray * n_total / (ms_total * 1e-3) / 1e9}
     print(json.dumps(out), flush=True)
     # brute force (the reference's algorithm) on 2 M rays for comparison and a bitwise check
     o, d = synth.random_rays(2_000_000, seed=5, chunk_offset=0)
