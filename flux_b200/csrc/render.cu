@@ -310,6 +310,11 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
     }
 }
 
+// largest chunk of rays per warp (measured r1, config 5 in 10 M-ray launches: 64 / 128 / 256 / 512 / 2048 rays ->
+// 1405 / 1460 / 1756 / 1782 / 1654 Mrays/s: small chunks pay the refill tail, large ones leave a ragged last wave)
+#ifndef TRACE_RPW_MAX
+#define TRACE_RPW_MAX 512
+#endif
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
                        int sm_count, cudaStream_t stream, unsigned long long *counters) {
     if (n == 0) return;
@@ -318,7 +323,7 @@ void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const do
     if (sc.use_bvh) {
         // chunk of rays per warp: large enough to amortise the refill tail, small enough for >= 16 warps per SM
         uint64_t rpw = (n + (uint64_t)sm_count * 16 - 1) / ((uint64_t)sm_count * 16);
-        rpw = rpw < 32 ? 32 : (rpw > 2048 ? 2048 : rpw);
+        rpw = rpw < 32 ? 32 : (rpw > TRACE_RPW_MAX ? TRACE_RPW_MAX : rpw);
         const uint64_t warps = (n + rpw - 1) / rpw;
         const size_t smem = (size_t)BVH_STACK * threads * sizeof(uint2);
         const int blocks = (int)((warps * 32 + threads - 1) / threads);
