@@ -89,8 +89,18 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """The host cores this process may run on.  Asked of the OS, not of OpenMP: torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would quietly turn the CPU arm into a single-threaded run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_run(root: int, threads: int = 0):
     """One full-frame render of demo2 on the CPU oracle at sample_root `root`; returns (seconds, Msamples/s)."""
+    threads = threads or host_threads()
     from flux_b200 import JobConfiguration, SceneData
     from oracle import oracle_py as O
     sd = SceneData.from_yaml(SCENE)
@@ -117,8 +127,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle_py as O
-    cores = O.num_threads()
+    cores = host_threads()
     root = args.cpu_root or pick_cpu_root(8.0)
     for _ in range(args.warmup):
         cpu_oracle_run(min(root, 8))
@@ -312,11 +321,10 @@ def main():
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            from oracle import oracle_py as O
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported on rank 0 at N = 1 only
             croot = args.cpu_root or pick_cpu_root(15.0)
             dt, msps = cpu_oracle_run(croot)
-            cpu = {"value": msps, "unit": "Msamples/s", "cores": O.num_threads(), "kind": "port",
+            cpu = {"value": msps, "unit": "Msamples/s", "cores": host_threads(), "kind": "port",
                    "sample": f"full 800x600 demo2 frame at sample_root {croot} ({croot * croot} spp), {dt:.1f} s; "
                              "C++/OpenMP oracle (Rust reference cannot be built here); Msamples/s is spp-independent",
                    "readme_reference": "5.314 Msamples/s on 44 cores (README.md:1)"}
