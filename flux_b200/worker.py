@@ -259,7 +259,7 @@ class GpuWorker:
         self.ctx = GpuContext(device)
         self.seed = seed
 
-    def info(self) -> dict:  # WorkerInfo, manager.rs:30-33
+    def info(self) -> dict:  # WorkerInfo, manager.rs:221-224 (num_threads) + a display name
         return {"name": f"gpu{self.ctx.device}", "num_threads": 1}
 
     def run_job(self, scene_data: SceneData, config: JobConfiguration, units: Optional[Iterable[WorkUnit]] = None,

@@ -69,7 +69,7 @@ struct WorkUnitResult {                                             // manager.r
     WorkUnit work_unit;
     std::vector<double> rows;   // [row_end-row_start+1][W][3], linear RGB, averaged and max_to_one-clamped
 };
-struct WorkerInfo { std::string name; uint32_t num_threads; };      // manager.rs:30-33
+struct WorkerInfo { std::string name; uint32_t num_threads; };      // manager.rs:221-224 (num_threads) + a display name that never travels
 
 // Owns the arrays a flux_scene_flat points into.
 struct FlatScene {
