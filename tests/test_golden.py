@@ -57,3 +57,37 @@ def test_oracle_matches_reference_render_statistically(demo2):
     assert rmse < 0.083, rmse
     assert block_rmse < 0.0225, block_rmse
     assert np.all(np.abs(ratio - 1.0) < 0.01), ratio
+
+
+def test_primary_hit_map_lines_up_with_the_reference_render(demo2):
+    """the oracle's primary-hit shape-id map of demo2 (pinhole rays through the pixel centres)
+    against the reference's own image.  demo.png shows only the ten glossy spheres and the floor (no sky, no light), so
+    the check is geometric: the luminance gradient of demo.png sits on the oracle's silhouettes of the spheres near
+    the focal plane (ids 3-6) — 12 x the image mean — and falls off when the map is shifted by 2, 3 or 4 pixels in
+    any of eight directions, or mirrored.  A wrong camera basis, aspect, zoom, row direction (trace.rs:72-73) or
+    sphere position fails this by a wide margin."""
+    from scipy import ndimage
+    flat = demo2.flatten()
+    H, W = 600, 800
+    o, d = np.empty((H, W, 3)), np.empty((H, W, 3))
+    for r in range(H):
+        for c in range(W):
+            o[r, c], d[r, c] = O.primary_ray(flat, r, c, 0.5, 0.5, 0.0, 0.0)     # lens sample (0, 0): pinhole
+    hit, _ = O.trace_rays(flat, o.reshape(-1, 3), d.reshape(-1, 3))
+    ids = hit.reshape(H, W)
+    assert set(np.unique(ids)) == set(range(2, 13))          # ten spheres and the floor; neither emitter is in view
+    lum = reference_image().mean(2)
+    grad = np.hypot(ndimage.sobel(lum, axis=1), ndimage.sobel(lum, axis=0))
+    edge = np.zeros((H, W), bool)
+    for sid in (3, 4, 5, 6):
+        m = ids == sid
+        edge |= m & ~ndimage.binary_erosion(m)
+    aligned = grad[edge].mean()
+    assert aligned > 10 * grad.mean(), (aligned, grad.mean())
+    for s in (2, 3, 4):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if (dy, dx) != (0, 0):
+                    shifted = grad[np.roll(np.roll(edge, dy * s, 0), dx * s, 1)].mean()
+                    assert shifted < 0.93 * aligned, (s, dy, dx, shifted, aligned)
+    assert grad[edge[:, ::-1]].mean() < 0.5 * aligned and grad[edge[::-1]].mean() < 0.5 * aligned
