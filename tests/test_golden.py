@@ -67,14 +67,8 @@ def test_primary_hit_map_lines_up_with_the_reference_render(demo2):
     any of eight directions, or mirrored.  A wrong camera basis, aspect, zoom, row direction (trace.rs:72-73) or
     sphere position fails this by a wide margin."""
     from scipy import ndimage
-    flat = demo2.flatten()
     H, W = 600, 800
-    o, d = np.empty((H, W, 3)), np.empty((H, W, 3))
-    for r in range(H):
-        for c in range(W):
-            o[r, c], d[r, c] = O.primary_ray(flat, r, c, 0.5, 0.5, 0.0, 0.0)     # lens sample (0, 0): pinhole
-    hit, _ = O.trace_rays(flat, o.reshape(-1, 3), d.reshape(-1, 3))
-    ids = hit.reshape(H, W)
+    ids = primary_hit_ids(demo2.flatten(), H, W)
     assert set(np.unique(ids)) == set(range(2, 13))          # ten spheres and the floor; neither emitter is in view
     lum = reference_image().mean(2)
     grad = np.hypot(ndimage.sobel(lum, axis=1), ndimage.sobel(lum, axis=0))
@@ -93,31 +87,50 @@ def test_primary_hit_map_lines_up_with_the_reference_render(demo2):
     assert grad[edge[:, ::-1]].mean() < 0.5 * aligned and grad[edge[::-1]].mean() < 0.5 * aligned
 
 
-def test_per_object_colours_match_the_reference_render(demo2):
-    """Mean colour of every sphere and of the floor (interior of the oracle's primary-hit regions, every 4th row),
-    oracle at 64 spp against demo.png: within 3 % per channel (measured: floor 0.5 %, spheres 0.2-2.4 %, of which
-    about 1 % is demo.png's 8-bit truncation).  Pins the per-sphere materials — the three glossy exponents and
-    colours cycle over the spheres — the emitters that light them and the floor's Lambertian term."""
-    from scipy import ndimage
-    flat = demo2.flatten()
-    H, W = 600, 800
-    rows = np.arange(0, H, 4)
+def primary_hit_ids(flat, H=600, W=800):
+    """Oracle shape id under every pixel centre, pinhole (lens sample (0, 0))."""
     oo, dd = np.empty((H, W, 3)), np.empty((H, W, 3))
     for r in range(H):
         for c in range(W):
             oo[r, c], dd[r, c] = O.primary_ray(flat, r, c, 0.5, 0.5, 0.0, 0.0)
-    full_ids = O.trace_rays(flat, oo.reshape(-1, 3), dd.reshape(-1, 3))[0].reshape(H, W)
-    cfg = JobConfiguration(8, 5, 50)
-    ss = O.generate_samples(1, 8, 5, W)
-    ss.set_index = O.generate_set_index(1, H, W, W)
-    img = O.render_row_list(flat, cfg, ss, rows)
-    ref = reference_image()[rows]
-    checked = 0
-    for sid in range(2, 13):
+    return O.trace_rays(flat, oo.reshape(-1, 3), dd.reshape(-1, 3))[0].reshape(H, W)
+
+
+def as_demo_png(img):
+    """What an 8-bit file holds for linear colour c: floor(c * 255.99), the conversion of flux/src/main.rs:261-263,
+    read back as v / 255.  Applied per pixel to a noisy render it lowers dark regions by up to 1.5 %."""
+    return np.floor(np.clip(img, 0.0, 1.0) * 255.99) / 255.0
+
+
+def per_object_ratios(img, ref, ids_rows, full_ids, rows, min_pixels=600):
+    from scipy import ndimage
+    out = {}
+    for sid in np.unique(full_ids):
         interior = ndimage.binary_erosion(full_ids == sid, iterations=4)[rows]    # away from defocused silhouettes
-        if interior.sum() < 600:
-            continue
-        a, b = img[interior].mean(0), ref[interior].mean(0)
-        assert np.all(np.abs(a / b - 1.0) < 0.03), (sid, a, b)
-        checked += 1
-    assert checked >= 8
+        if interior.sum() >= min_pixels:
+            out[int(sid)] = img[interior].mean(0) / ref[interior].mean(0) - 1.0
+    return out
+
+
+def test_per_object_colours_match_the_reference_render(demo2):
+    """Mean colour of every sphere and of the floor (interior of the oracle's primary-hit regions, every 4th row):
+    the oracle at 1024 spp, quantised the way demo.png was, against demo.png.  Measured: every object within 0.15 %
+    per channel, the whole image within 0.1 %; asserted at 0.5 % / 0.3 %.  This pins — against the reference's own
+    output — the three glossy materials that cycle over the spheres, both emitters, the Lambertian floor with its
+    uniform-hemisphere quirk, the lens, max_to_one and the trace depth to well below anything a modelling error
+    would leave (one wrong exponent, a cosine-weighted hemisphere or a missing 1/pi each move an object by > 5 %)."""
+    flat = demo2.flatten()
+    H, W = 600, 800
+    rows = np.arange(2, H, 4)
+    full_ids = primary_hit_ids(flat, H, W)
+    cfg = JobConfiguration(32, 5, 50)
+    ss = O.generate_samples(3, 32, 5, W)
+    ss.set_index = O.generate_set_index(3, H, W, W)
+    img = as_demo_png(O.render_row_list(flat, cfg, ss, rows))
+    ref = reference_image()[rows]
+    ratios = per_object_ratios(img, ref, None, full_ids, rows)
+    assert len(ratios) >= 8 and 12 in ratios
+    for sid, r in ratios.items():
+        assert np.all(np.abs(r) < 0.005), (sid, r)
+    whole = img.reshape(-1, 3).mean(0) / ref.reshape(-1, 3).mean(0) - 1.0
+    assert np.all(np.abs(whole) < 0.003), whole
