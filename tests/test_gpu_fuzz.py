@@ -139,3 +139,44 @@ def test_random_scenes_bvh_equals_linear_and_oracle(gpu_ctx, seed):
     ho, to = O.trace_rays(flat, o[:20_000], d[:20_000])
     assert np.array_equal(res[2][0][:20_000], ho)
     assert np.array_equal(res[2][1][:20_000].view(np.uint64), to.view(np.uint64))
+
+
+@pytest.mark.parametrize("seed", range(400, 408))
+def test_random_scenes_with_triangles_boxes_and_rectangles_render_like_the_oracle(gpu_ctx, seed):
+    """Random mixed scenes — spheres, planes, loose triangles, boxes, rectangles, a small mesh, all four material
+    kinds — rendered through the BVH by every kernel that takes triangles, and by the linear-scan direct kernel."""
+    from flux_b200 import BoxData, MeshData, RectangleData
+    rng = np.random.default_rng(seed)
+    sd0 = random_scene(seed, allow_glossy=True)
+    shapes = list(sd0.shapes)
+    for _ in range(int(rng.integers(3, 30))):
+        a = rng.uniform(-5, 5, 3)
+        shapes.append(TriangleData(tuple(map(float, a)), tuple(map(float, a + rng.standard_normal(3) * 10.0 ** rng.uniform(-1, 0.5))),
+                                   tuple(map(float, a + rng.standard_normal(3) * 10.0 ** rng.uniform(-1, 0.5))), _material(rng, True)))
+    for _ in range(int(rng.integers(1, 4))):
+        lo = rng.uniform(-4, 3, 3)
+        shapes.append(BoxData(tuple(map(float, lo)), tuple(map(float, lo + rng.uniform(0.2, 2.0, 3))), _material(rng, True)))
+    for _ in range(int(rng.integers(1, 3))):
+        c = rng.uniform(-4, 4, 3)
+        shapes.append(RectangleData(tuple(map(float, c)), tuple(map(float, rng.standard_normal(3) * 2)), tuple(map(float, rng.standard_normal(3) * 2)),
+                                    _material(rng, True)))
+    verts = rng.uniform(-3, 3, (12, 3))
+    faces = np.array([rng.choice(12, 3, replace=False) for _ in range(10)])
+    shapes.append(MeshData(verts, faces, _material(rng, True)))
+    shapes = [shapes[i] for i in rng.permutation(len(shapes))]
+    sd = SceneData(f"fuzzmix{seed}", sd0.output_settings, sd0.background, shapes, sd0.camera_settings, sd0.camera_data)
+    cfg = JobConfiguration(16, 5, 50)
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(seed, cfg, 20, 14)
+    ref = O.render_rows(flat, cfg, ss, 0, 13)
+    try:
+        for accel, modes in ((2, (1, 2, 4)), (1, (1,))):
+            gpu_ctx.set_accel_mode(accel)
+            Hp.upload(gpu_ctx, flat, cfg, ss)
+            for mode in modes:
+                gpu_ctx.set_kernel_mode(mode)
+                img = gpu_ctx.render_rows(0, 13, 20)
+                assert Hp.rel_err(img, ref) <= 1e-6, (accel, mode)
+    finally:
+        gpu_ctx.set_kernel_mode(0)
+        gpu_ctx.set_accel_mode(0)
