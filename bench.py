@@ -267,6 +267,13 @@ def main():
             ctx.render_row_list(my_rows, W, out=out_host)
         barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the frame of the last e2e step, as rank 0 holds it: the same bytes whatever the number of GPUs (SURVEY.md §4:
+    # sharding must not change per-pixel arithmetic), so the N = 1, 2, 4, 8 lines can be compared
+    frame_sha256 = None
+    if rank == 0:
+        import hashlib
+        final = host_frame.numpy() if world > 1 else out_host
+        frame_sha256 = hashlib.sha256(np.ascontiguousarray(final).tobytes()).hexdigest()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,6 +341,7 @@ def main():
             "scaling": "strong", "vs_baseline": value / 5.314, "dtype": "f64", "data": "synthetic",
             "config": workload_config(root, world), "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+            "frame_sha256": frame_sha256,
             "render_time_s_16384spp": W * H * 16384 / (value * 1e6),
             "vs_baseline_note": "value / 5.314 Msamples/s = README.md:1 (1479.9 s, 44 cores, unknown CPU)",
         }
