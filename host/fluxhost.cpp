@@ -749,6 +749,62 @@ std::vector<WorkUnitResult> GpuWorker::run_job(const SceneData &sd, const JobCon
     return out;
 }
 
+Image GpuWorker::render_job_progressive(const SceneData &sd, const JobConfiguration &cfg, uint32_t batch,
+                                        const std::function<bool(uint32_t, const Image &)> &on_pass) {
+    if (batch == 0) throw Error("render_job_progressive: batch must be >= 1");
+    const uint32_t W = sd.output_settings.image_width, H = sd.output_settings.image_height;
+    const uint32_t n = cfg.sample_root * cfg.sample_root;
+    const uint32_t world = (uint32_t)devices_.size();
+    const size_t row_elems = (size_t)W * 3;
+    Image img(W, H);
+    Scene scene = Scene::from_data(sd, cfg);
+    std::vector<std::vector<uint32_t>> rows(world);
+    std::vector<std::vector<double>> px(world);
+    std::vector<std::string> errors(world);
+    auto on_every_gpu = [&](const std::function<void(uint32_t)> &f) {
+        auto guarded = [&](uint32_t rank) {
+            try {
+                f(rank);
+            } catch (const std::exception &e) {
+                errors[rank] = e.what();
+            }
+        };
+        if (world == 1) {
+            guarded(0);
+        } else {
+            std::vector<std::thread> th;
+            for (uint32_t r = 0; r < world; r++) th.emplace_back(guarded, r);
+            for (auto &t : th) t.join();
+        }
+        for (const std::string &e : errors)
+            if (!e.empty()) throw Error(e);
+    };
+    on_every_gpu([&](uint32_t rank) {   // Scene::from_data + Camera::new, then name this GPU's rows
+        uint32_t cnt = 0;
+        flux_shard_rows(H, tile_rows_, rank, world, nullptr, &cnt);
+        rows[rank].resize(cnt);
+        flux_shard_rows(H, tile_rows_, rank, world, rows[rank].data(), &cnt);
+        px[rank].resize(cnt * row_elems);
+        GpuContext &ctx = *contexts_[rank];
+        Camera::create(ctx, scene, cfg, W, seed_);
+        ctx.check(flux_progressive_begin(ctx.get(), rows[rank].data(), cnt), "flux_progressive_begin");
+    });
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t end = std::min(n, done + batch);
+        on_every_gpu([&](uint32_t rank) {
+            if (rows[rank].empty()) return;
+            GpuContext &ctx = *contexts_[rank];
+            ctx.check(flux_progressive_pass(ctx.get(), done, end, px[rank].data()), "flux_progressive_pass");
+            for (size_t k = 0; k < rows[rank].size(); k++)   // disjoint rows: no synchronisation needed
+                std::copy(px[rank].begin() + k * row_elems, px[rank].begin() + (k + 1) * row_elems,
+                          img.pixels.begin() + (size_t)rows[rank][k] * row_elems);
+        });
+        done = end;
+        if (on_pass && !on_pass(done, img)) break;
+    }
+    return img;
+}
+
 void GpuWorker::begin_job(const SceneData &sd, const JobConfiguration &cfg) {
     auto job = std::make_unique<ActiveJob>();
     job->scene = Scene::from_data(sd, cfg);

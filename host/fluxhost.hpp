@@ -176,6 +176,11 @@ class GpuWorker {
     // the same loop body driven from outside, the way a manager drives a worker over its unit channel
     // (workers.rs:46-71; flux-node/src/main.rs:60-75): begin_job = Scene::from_data + Camera::new on every GPU,
     // render_unit = camera.render(&scene, unit) with the unit's rows sharded over the GPUs in interleaved tiles.
+    // Progressive refinement of the whole frame: passes of `batch` samples per pixel on every
+    // GPU's row shard; after each pass on_pass(samples_done, image_so_far) is called and returns false to cancel
+    // (the preview's Esc -> JobHandle::cancel, flux/src/main.rs:288-293).  Returns the last image.
+    Image render_job_progressive(const SceneData &sd, const JobConfiguration &cfg, uint32_t batch,
+                                 const std::function<bool(uint32_t, const Image &)> &on_pass);
     void begin_job(const SceneData &sd, const JobConfiguration &cfg);
     bool has_job() const { return job_ != nullptr; }
     WorkUnitResult render_unit(const WorkUnit &unit);

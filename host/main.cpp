@@ -1,6 +1,7 @@
 // fluxb200 — render driver mirroring the reference's `flux` binary (flux/src/main.rs:23-205) for the GPU path:
 //
 //   fluxb200 <scene_file> [-r ROOT] [-d DEPTH] [-R COUNT] [-G GPUS] [--seed S] [--width W --height H] [-o FILE]
+//            [--progressive K] [-n ADDRESS[:PORT]]
 //
 // -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node ADDRESS[:PORT]
 // renders on a fluxb200-node (or flux-node) process instead of the local GPUs, speaking the reference's network
@@ -8,6 +9,8 @@
 // counterpart: there is no local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
 // (manager.rs:330) unless -o is given.  --dump-flat FILE writes the flattened scene (no GPU needed; used by the
 // tests to compare this loader with the Python mirror).
+#include <chrono>
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +22,8 @@
 
 namespace {
 
+volatile std::sig_atomic_t g_interrupted = 0;
+
 struct Config {   // flux/src/main.rs:114-124
     std::string input_filename, output_filename, dump_flat, node;
     uint32_t sample_root = 1, max_depth = 5, rows_per_work_unit = 50;
@@ -26,6 +31,7 @@ struct Config {   // flux/src/main.rs:114-124
     uint64_t seed = 1;
     std::vector<int> devices;
     bool enum_map = false;
+    uint32_t progressive = 0;
 };
 
 [[noreturn]] void usage(const char *msg) {
@@ -38,6 +44,7 @@ struct Config {   // flux/src/main.rs:114-124
                  "    -R, --rows <COUNT>     Image rows per work unit [default: 50]\n"
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
                  "        --devices <LIST>   Explicit CUDA device list instead of -G, e.g. 0,2,3\n"
+                 "        --progressive <K>  Refine the frame in passes of K samples per pixel; Ctrl-C keeps what is done\n"
                  "    -n, --node <ADDRESS[:PORT]>   Render using the fluxb200-node / flux-node process at this address\n"
                  "        --enum-form <array|map>   With -n: CBOR form of enum variants, serde_cbor < 0.10 (default) or >= 0.10\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
@@ -67,6 +74,7 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-d" || a == "--depth") c.max_depth = (uint32_t)parse_u64(next("--depth"), "--depth");
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
+        else if (a == "--progressive") c.progressive = (uint32_t)parse_u64(next("--progressive"), "--progressive");
         else if (a == "-n" || a == "--node") c.node = next("--node");
         else if (a == "--enum-form") {   // with -n: how enum variants are written (see host/fluxnet.hpp)
             const std::string f = next("--enum-form");
@@ -135,6 +143,27 @@ int main(int argc, char **argv) {
         jobcfg.rows_per_work_unit = config.rows_per_work_unit;
         std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),   // title(), main.rs:207-214
                     jobcfg.sample_root * jobcfg.sample_root, jobcfg.sample_root == 1 ? "" : "s", jobcfg.max_trace_depth);
+        if (config.progressive) {
+            // the preview's refinement and Esc (flux/src/main.rs:288-315) without the window: every pass improves
+            // the whole frame; an interrupt stops after the pass in flight and the image so far is written
+            std::signal(SIGINT, [](int) { g_interrupted = 1; });
+            const auto t0 = std::chrono::steady_clock::now();
+            uint32_t samples = 0;
+            flux::Image img = worker.render_job_progressive(s, jobcfg, config.progressive, [&](uint32_t done, const flux::Image &) {
+                samples = done;
+                std::printf("pass to %u samples per pixel, %.3fs\n", done,
+                            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+                std::fflush(stdout);
+                return !g_interrupted;
+            });
+            const uint32_t total = jobcfg.sample_root * jobcfg.sample_root;
+            if (samples < total) std::printf("cancelled after %u of %u samples per pixel\n", samples, total);
+            else std::printf("rendering finished, total time %.6fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
+            img.write(out);
+            std::printf("wrote %s\nShutting down\n", out.c_str());
+            return 0;
+        }
         double seconds = 0.0;
         flux::Image img = worker.render_job(s, jobcfg, &seconds);
         std::printf("rendering finished, total time %.6fs\n", seconds);   // manager.rs:327

@@ -108,3 +108,40 @@ def test_camera_render_progressive_and_cancel():
         for done, res in cam.render_progressive(scene, unit, 10, cancel=lambda: len(seen) >= 2):
             seen.append(done)
         assert seen == [10, 20]
+
+
+def _read_ppm(path):
+    tok = open(path).read().split()
+    assert tok[0] == "P3"
+    w, h, mx = int(tok[1]), int(tok[2]), int(tok[3])
+    return np.array(tok[4:], dtype=np.int64).reshape(h, w, 3), mx
+
+
+def test_cli_progressive_refines_to_the_one_shot_frame(tmp_path):
+    """`fluxb200 --progressive K` (the preview's refinement without the window): passes on two row shards (two
+    contexts on this GPU) end at the frame the one-shot render writes — the 16-bit PPM values differ by at most one
+    unit, and only where the different order of the per-pixel sum crosses a quantisation step."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "host"), "-s"], check=True)
+    cli, scene = os.path.join(root, "host", "fluxb200"), os.path.join(root, "scenes", "demo2.yml")
+    common = ["-r", "6", "--width", "64", "--height", "48", "--seed", "5"]
+    a = subprocess.run([cli, scene, *common, "--progressive", "10", "--devices", "0,0", "-o", str(tmp_path / "prog.ppm")],
+                       capture_output=True, timeout=300)
+    assert a.returncode == 0, a.stderr.decode()
+    out = a.stdout.decode()
+    assert [int(l.split()[2]) for l in out.splitlines() if l.startswith("pass to")] == [10, 20, 30, 36]
+    assert "rendering finished" in out and "cancelled" not in out
+    b = subprocess.run([cli, scene, *common, "-o", str(tmp_path / "once.ppm")], capture_output=True, timeout=300)
+    assert b.returncode == 0, b.stderr.decode()
+    p, mx = _read_ppm(tmp_path / "prog.ppm")
+    q, _ = _read_ppm(tmp_path / "once.ppm")
+    assert mx == 65535 and p.shape == q.shape == (48, 64, 3)
+    diff = np.abs(p - q)
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    # one pass over everything is the direct kernel's frame exactly; a first pass alone is a coarser image of it
+    c = subprocess.run([cli, scene, *common, "--progressive", "36", "-o", str(tmp_path / "single.ppm")], capture_output=True, timeout=300)
+    assert c.returncode == 0 and c.stdout.decode().count("pass to") == 1
+    s, _ = _read_ppm(tmp_path / "single.ppm")
+    assert np.abs(s - q).max() <= 1
