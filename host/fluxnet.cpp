@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -604,7 +605,18 @@ NetworkWorker::~NetworkWorker() {
     if (fd_ >= 0) ::close(fd_);
 }
 
-Image NetworkWorker::render_job(const Job &job) {
+bool UnitQueue::pop(WorkUnit &u) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (next_ >= units_.size()) return false;
+    u = units_[next_++];
+    return true;
+}
+
+UnitQueue::UnitQueue(const Job &job) : units_(work_units(job.scene_data.output_settings.image_height, job.config.rows_per_work_unit, job.id.id)) {
+    for (WorkUnit &u : units_) u.job_allocator_id = job.id.allocator_id;
+}
+
+void NetworkWorker::run(const Job &job, UnitQueue &queue, Image &img) {
     if (fd_ < 0) throw Error("NetworkWorker: connection already used (the node ends it after Done)");
     FdSource src(fd_);
     cbor::Reader reader(src);
@@ -613,10 +625,7 @@ Image NetworkWorker::render_job(const Job &job) {
     if (!reader.next(node)) throw Error("Could not get info from network node");
     info_ = WorkerInfo{"NetworkWorker(" + endpoint_ + ")", (uint32_t)worker_info_from(node)};
 
-    const uint32_t W = job.scene_data.output_settings.image_width, H = job.scene_data.output_settings.image_height;
-    Image img(W, H);
-    std::vector<WorkUnit> units = work_units(H, job.config.rows_per_work_unit, job.id.id);
-    for (WorkUnit &u : units) u.job_allocator_id = job.id.allocator_id;
+    const uint32_t W = job.scene_data.output_settings.image_width;
     send_all(fd_, encode_set_job(job, form_));
     auto collect = [&] {
         if (!reader.next(node)) throw Error("network node closed the connection before all results arrived");
@@ -625,20 +634,57 @@ Image NetworkWorker::render_job(const Job &job) {
         if (w != W) throw Error("network node returned rows of another width");
         if (r.work_unit.job_id != job.id.id || r.work_unit.job_allocator_id != job.id.allocator_id)
             throw Error("network node returned rows of another job");
-        img.set_rows(r);
+        img.set_rows(r);   // units are disjoint row ranges: workers sharing an Image never touch the same bytes
     };
-    // two units in flight (workers.rs:160-175), then one result per further unit, then the tail
-    size_t sent = 0, received = 0;
-    for (; sent < units.size() && sent < 2; sent++) send_all(fd_, encode_work_unit(units[sent], form_));
-    for (; sent < units.size(); sent++) {
-        send_all(fd_, encode_work_unit(units[sent], form_));
-        collect();
-        received++;
+    // two units in flight (workers.rs:160-175), then one more unit per result while the shared queue has any
+    // (the reference's workers pull from one bounded queue the same way, manager.rs:100,156-162), then the tail
+    size_t in_flight = 0;
+    WorkUnit u{0, 0, 0, 0};
+    while (in_flight < 2 && queue.pop(u)) {
+        send_all(fd_, encode_work_unit(u, form_));
+        in_flight++;
     }
-    for (; received < units.size(); received++) collect();
+    while (in_flight) {
+        if (queue.pop(u)) {
+            send_all(fd_, encode_work_unit(u, form_));
+            in_flight++;
+        }
+        collect();
+        in_flight--;
+    }
     send_all(fd_, encode_done());
     ::close(fd_);
     fd_ = -1;
+}
+
+Image NetworkWorker::render_job(const Job &job) {
+    Image img(job.scene_data.output_settings.image_width, job.scene_data.output_settings.image_height);
+    UnitQueue queue(job);
+    run(job, queue, img);
+    return img;
+}
+
+Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &job, EnumForm form, std::vector<WorkerInfo> *infos) {
+    if (endpoints.empty()) throw Error("render_job_on_nodes: no endpoints");
+    Image img(job.scene_data.output_settings.image_width, job.scene_data.output_settings.image_height);
+    UnitQueue queue(job);
+    std::vector<std::unique_ptr<NetworkWorker>> workers;
+    for (const std::string &e : endpoints) workers.push_back(std::make_unique<NetworkWorker>(e, form));   // connect first: fail early
+    std::vector<std::string> errors(workers.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < workers.size(); i++)
+        th.emplace_back([&, i] {
+            try {
+                workers[i]->run(job, queue, img);
+            } catch (const std::exception &e) {
+                errors[i] = e.what();   // like the reference, a lost node is fatal for the job (manager.rs:158-161)
+            }
+        });
+    for (auto &t : th) t.join();
+    for (const std::string &e : errors)
+        if (!e.empty()) throw Error(e);
+    if (infos)
+        for (auto &w : workers) infos->push_back(w->info());
     return img;
 }
 

@@ -20,6 +20,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -76,6 +77,19 @@ class NodeServer {
     std::atomic<bool> stop_{false};
 };
 
+// The work units of one job, handed out one at a time to whoever asks: the shared bounded(1) queue the
+// reference's workers pull from (manager.rs:100,156-162).
+class UnitQueue {
+  public:
+    explicit UnitQueue(const Job &job);   // work_units() of the job, in row order
+    bool pop(WorkUnit &u);                // thread-safe; false when every unit has been handed out
+
+  private:
+    std::mutex mu_;
+    std::vector<WorkUnit> units_;
+    size_t next_ = 0;
+};
+
 // ---- the manager's end (workers.rs:118-245) ----
 class NetworkWorker {
   public:
@@ -87,6 +101,8 @@ class NetworkWorker {
     // one job over the connection: SetJob, two units in flight, one RowsReady per unit, Done (which ends the
     // connection: flux-node returns from handle_client on Done)
     Image render_job(const Job &job);
+    // the same, taking units from a queue shared with other workers and writing rows into a shared image
+    void run(const Job &job, UnitQueue &queue, Image &img);
 
   private:
     int fd_ = -1;
@@ -94,6 +110,10 @@ class NetworkWorker {
     std::string endpoint_;
     EnumForm form_;
 };
+
+// One job over several nodes (`flux -n a -n b`): every node gets the job, all pull units from one queue.
+Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &job, EnumForm form = EnumForm::Array,
+                          std::vector<WorkerInfo> *infos = nullptr);
 
 }  // namespace net
 }  // namespace flux

@@ -4,8 +4,8 @@
 //            [--progressive K] [-n ADDRESS[:PORT]]
 //
 // -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node ADDRESS[:PORT]
-// renders on a fluxb200-node (or flux-node) process instead of the local GPUs, speaking the reference's network
-// protocol (workers.rs:118-245); one node, since a node ends the connection after a job.  -L, -g and -t have no
+// renders on fluxb200-node (or flux-node) processes instead of the local GPUs, speaking the reference's network
+// protocol (workers.rs:118-245); given several times, the nodes share the job's work units through one queue.  -L, -g and -t have no
 // counterpart: there is no local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
 // (manager.rs:330) unless -o is given.  --dump-flat FILE writes the flattened scene (no GPU needed; used by the
 // tests to compare this loader with the Python mirror).
@@ -25,7 +25,8 @@ namespace {
 volatile std::sig_atomic_t g_interrupted = 0;
 
 struct Config {   // flux/src/main.rs:114-124
-    std::string input_filename, output_filename, dump_flat, node;
+    std::string input_filename, output_filename, dump_flat;
+    std::vector<std::string> nodes;   // -n may be given several times (flux/src/main.rs:131-137)
     uint32_t sample_root = 1, max_depth = 5, rows_per_work_unit = 50;
     uint32_t gpus = 1, width = 0, height = 0;
     uint64_t seed = 1;
@@ -75,7 +76,7 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
         else if (a == "--progressive") c.progressive = (uint32_t)parse_u64(next("--progressive"), "--progressive");
-        else if (a == "-n" || a == "--node") c.node = next("--node");
+        else if (a == "-n" || a == "--node") c.nodes.push_back(next("--node"));
         else if (a == "--enum-form") {   // with -n: how enum variants are written (see host/fluxnet.hpp)
             const std::string f = next("--enum-form");
             if (f != "array" && f != "map") usage("--enum-form takes array or map");
@@ -120,12 +121,13 @@ int main(int argc, char **argv) {
         netcfg.sample_root = config.sample_root;
         netcfg.max_trace_depth = config.max_depth;
         netcfg.rows_per_work_unit = config.rows_per_work_unit;
-        if (!config.node.empty()) {
-            flux::net::NetworkWorker node(config.node, config.enum_map ? flux::net::EnumForm::Map : flux::net::EnumForm::Array);
+        if (!config.nodes.empty()) {
             std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),
                         netcfg.sample_root * netcfg.sample_root, netcfg.sample_root == 1 ? "" : "s", netcfg.max_trace_depth);
-            flux::Image img = node.render_job(flux::Job{flux::JobID{config.seed, 0}, s, netcfg});
-            std::printf("Network worker ready, info:\nThreads: %u\n", node.info().num_threads);
+            std::vector<flux::WorkerInfo> infos;
+            flux::Image img = flux::net::render_job_on_nodes(config.nodes, flux::Job{flux::JobID{config.seed, 0}, s, netcfg},
+                                                             config.enum_map ? flux::net::EnumForm::Map : flux::net::EnumForm::Array, &infos);
+            for (const flux::WorkerInfo &wi : infos) std::printf("%s ready, info:\nThreads: %u\n", wi.name.c_str(), wi.num_threads);
             const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
             img.write(out);
             std::printf("wrote %s\nShutting down\n", out.c_str());

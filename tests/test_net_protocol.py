@@ -324,3 +324,55 @@ def test_python_network_worker_drives_a_node(form):
     assert fake.error is None, fake.error
     assert [e[1:3] for e in fake.events[1:-1]] == [(0, 3), (4, 7), (8, 8)]
     assert np.array_equal(img, np.array([[FakeNode.colour(r, c) for c in range(10)] for r in range(9)]))
+
+
+def test_cpp_manager_shares_one_job_between_two_nodes(node, tmp_path):
+    """`fluxb200 -n a -n b` (flux/src/main.rs:131-137: -n is repeatable): both nodes get the job, the work units are
+    handed out one at a time from a single queue (manager.rs:100), every unit is rendered exactly once and the rows
+    land where they belong."""
+    import ctypes
+    from flux_b200 import _capi
+    fakes = [FakeNode(num_threads=2), FakeNode(num_threads=7)]
+    out = tmp_path / "two.ppm"
+    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"),
+                        "-n", f"127.0.0.1:{fakes[0].port}", "-n", f"127.0.0.1:{fakes[1].port}",
+                        "-r", "2", "-R", "3", "--width", "24", "--height", "31", "--seed", "4", "-o", str(out)],
+                       capture_output=True, timeout=120)
+    for f in fakes:
+        f.thread.join(10)
+        assert f.error is None, f.error
+    assert p.returncode == 0, p.stderr.decode()
+    assert b"Threads: 2" in p.stdout and b"Threads: 7" in p.stdout
+    units = []
+    for f in fakes:
+        assert f.events[0][0] == "SetJob" and f.events[0][1] == (4, 0) and f.events[-1] == "Done"
+        units += [e[1:3] for e in f.events[1:-1]]
+    assert sorted(units) == [(r, min(30, r + 2)) for r in range(0, 31, 3)]          # each unit once, none lost
+    assert all(len(f.events) > 2 for f in fakes)                                       # both nodes took part
+    img = np.array([[FakeNode.colour(r, c) for c in range(24)] for r in range(31)], np.float64)
+    ref = tmp_path / "ref.ppm"
+    assert _capi.lib().flux_write_ppm(str(ref).encode(), 24, 31, img.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+    assert out.read_bytes() == ref.read_bytes()
+
+
+def test_cpp_manager_reports_a_node_that_goes_away(node, tmp_path):
+    """A node that closes the connection in the middle of a job is fatal for the job, as in the reference
+    (manager.rs:158-161 panics on a lost worker): exit status 101 and a message, no partial file."""
+    import socket
+    import threading
+    srv = socket.create_server(("127.0.0.1", 0))
+
+    def rude():
+        conn, _ = srv.accept()
+        conn.sendall(N.worker_info(1))
+        conn.recv(4096)
+        conn.close()
+
+    t = threading.Thread(target=rude, daemon=True)
+    t.start()
+    out = tmp_path / "gone.ppm"
+    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-n", f"127.0.0.1:{srv.getsockname()[1]}",
+                        "--width", "8", "--height", "8", "-o", str(out)], capture_output=True, timeout=120)
+    t.join(10)
+    assert p.returncode == 101 and (b"closed the connection" in p.stderr or b"send:" in p.stderr or b"recv:" in p.stderr), p.stderr
+    assert not out.exists()
