@@ -664,14 +664,25 @@ Image NetworkWorker::render_job(const Job &job) {
     return img;
 }
 
-Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &job, EnumForm form, std::vector<WorkerInfo> *infos) {
-    if (endpoints.empty()) throw Error("render_job_on_nodes: no endpoints");
+Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &job, EnumForm form, std::vector<WorkerInfo> *infos,
+                          GpuWorker *local) {
+    if (endpoints.empty() && !local) throw Error("render_job_on_nodes: no workers");
     Image img(job.scene_data.output_settings.image_width, job.scene_data.output_settings.image_height);
     UnitQueue queue(job);
     std::vector<std::unique_ptr<NetworkWorker>> workers;
     for (const std::string &e : endpoints) workers.push_back(std::make_unique<NetworkWorker>(e, form));   // connect first: fail early
-    std::vector<std::string> errors(workers.size());
+    std::vector<std::string> errors(workers.size() + 1);
     std::vector<std::thread> th;
+    if (local)
+        th.emplace_back([&] {
+            try {   // the LocalWorker loop, workers.rs:46-71
+                local->begin_job(job.scene_data, job.config);
+                WorkUnit u{0, 0, 0, 0};
+                while (queue.pop(u)) img.set_rows(local->render_unit(u));
+            } catch (const std::exception &e) {
+                errors[workers.size()] = e.what();
+            }
+        });
     for (size_t i = 0; i < workers.size(); i++)
         th.emplace_back([&, i] {
             try {
@@ -683,8 +694,10 @@ Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &
     for (auto &t : th) t.join();
     for (const std::string &e : errors)
         if (!e.empty()) throw Error(e);
-    if (infos)
+    if (infos) {
+        if (local) infos->push_back(local->info());
         for (auto &w : workers) infos->push_back(w->info());
+    }
     return img;
 }
 

@@ -111,9 +111,12 @@ class NetworkWorker {
     EnumForm form_;
 };
 
-// One job over several nodes (`flux -n a -n b`): every node gets the job, all pull units from one queue.
+// One job over several nodes (`flux -n a -n b`): every node gets the job, all pull units from one queue.  With
+// `local`, the GPUs of this box pull from the same queue (the reference's LocalWorker beside its NetworkWorkers,
+// flux/src/main.rs:43-60; `-L` leaves it out).  Which worker renders a unit is a matter of timing, as in the
+// reference; with the same seed on every worker the frame does not depend on it.
 Image render_job_on_nodes(const std::vector<std::string> &endpoints, const Job &job, EnumForm form = EnumForm::Array,
-                          std::vector<WorkerInfo> *infos = nullptr);
+                          std::vector<WorkerInfo> *infos = nullptr, GpuWorker *local = nullptr);
 
 }  // namespace net
 }  // namespace flux

@@ -5,7 +5,8 @@
 //
 // -r/--root, -d/--depth and -R/--rows keep the reference's meaning and defaults (1, 5, 50).  -n/--node ADDRESS[:PORT]
 // renders on fluxb200-node (or flux-node) processes instead of the local GPUs, speaking the reference's network
-// protocol (workers.rs:118-245); given several times, the nodes share the job's work units through one queue.  -L, -g and -t have no
+// protocol (workers.rs:118-245); given several times, the nodes share the job's work units through one queue, and
+// so do the GPUs of this box unless -L is given (the reference's local worker, main.rs:43-60).  -L, -g and -t have no
 // counterpart: there is no local CPU worker and no SDL preview.  The image is written to <scene_name>.ppm like ImageBuilder does
 // (manager.rs:330) unless -o is given.  --dump-flat FILE writes the flattened scene (no GPU needed; used by the
 // tests to compare this loader with the Python mirror).
@@ -14,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -31,7 +33,7 @@ struct Config {   // flux/src/main.rs:114-124
     uint32_t gpus = 1, width = 0, height = 0;
     uint64_t seed = 1;
     std::vector<int> devices;
-    bool enum_map = false;
+    bool enum_map = false, skip_local = false;
     uint32_t progressive = 0;
 };
 
@@ -46,6 +48,7 @@ struct Config {   // flux/src/main.rs:114-124
                  "    -G, --gpus <N>         GPUs of this box to render on [default: 1]\n"
                  "        --devices <LIST>   Explicit CUDA device list instead of -G, e.g. 0,2,3\n"
                  "        --progressive <K>  Refine the frame in passes of K samples per pixel; Ctrl-C keeps what is done\n"
+                 "    -L                     Do not use the GPUs of this box for rendering (with -n)\n"
                  "    -n, --node <ADDRESS[:PORT]>   Render using the fluxb200-node / flux-node process at this address\n"
                  "        --enum-form <array|map>   With -n: CBOR form of enum variants, serde_cbor < 0.10 (default) or >= 0.10\n"
                  "        --seed <S>         Seed of the sample sets [default: 1]\n"
@@ -75,6 +78,7 @@ Config config_from_args(int argc, char **argv) {
         else if (a == "-d" || a == "--depth") c.max_depth = (uint32_t)parse_u64(next("--depth"), "--depth");
         else if (a == "-R" || a == "--rows") c.rows_per_work_unit = (uint32_t)parse_u64(next("--rows"), "--rows");
         else if (a == "-G" || a == "--gpus") c.gpus = (uint32_t)parse_u64(next("--gpus"), "--gpus");
+        else if (a == "-L") c.skip_local = true;   // flux/src/main.rs:150-153
         else if (a == "--progressive") c.progressive = (uint32_t)parse_u64(next("--progressive"), "--progressive");
         else if (a == "-n" || a == "--node") c.nodes.push_back(next("--node"));
         else if (a == "--enum-form") {   // with -n: how enum variants are written (see host/fluxnet.hpp)
@@ -125,8 +129,16 @@ int main(int argc, char **argv) {
             std::printf("flux render (%s, %u sample%s per pixel, max depth %u)\n", s.scene_name.c_str(),
                         netcfg.sample_root * netcfg.sample_root, netcfg.sample_root == 1 ? "" : "s", netcfg.max_trace_depth);
             std::vector<flux::WorkerInfo> infos;
+            std::unique_ptr<flux::GpuWorker> local;   // the local worker renders beside the nodes unless -L (main.rs:43-60)
+            if (!config.skip_local) {
+                std::vector<int> devices = config.devices;
+                if (devices.empty())
+                    for (uint32_t g = 0; g < config.gpus; g++) devices.push_back((int)g);
+                local = std::make_unique<flux::GpuWorker>(devices, config.seed);
+            }
             flux::Image img = flux::net::render_job_on_nodes(config.nodes, flux::Job{flux::JobID{config.seed, 0}, s, netcfg},
-                                                             config.enum_map ? flux::net::EnumForm::Map : flux::net::EnumForm::Array, &infos);
+                                                             config.enum_map ? flux::net::EnumForm::Map : flux::net::EnumForm::Array, &infos,
+                                                             local.get());
             for (const flux::WorkerInfo &wi : infos) std::printf("%s ready, info:\nThreads: %u\n", wi.name.c_str(), wi.num_threads);
             const std::string out = config.output_filename.empty() ? s.scene_name + ".ppm" : config.output_filename;
             img.write(out);

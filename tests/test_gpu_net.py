@@ -70,7 +70,7 @@ def test_cpp_manager_over_the_node_writes_the_local_ppm(tmp_path):
     common = ["-r", "4", "-R", "9", "--width", "64", "--height", "48", "--seed", "3"]
     proc, port = start_node("--seed", "3")
     try:
-        a = subprocess.run([cli, scene, "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
+        a = subprocess.run([cli, scene, "-L", "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
         assert a.returncode == 0, a.stderr.decode()
         assert proc.wait(30) == 0
     finally:
@@ -126,7 +126,7 @@ def test_sharded_worker_paths_render_the_same_pixels(tmp_path):
     assert (tmp_path / "three.ppm").read_bytes() == (tmp_path / "one.ppm").read_bytes()
     proc, port = start_node("--seed", "8", "--devices", "0,0")
     try:
-        net = subprocess.run([cli, scene, "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
+        net = subprocess.run([cli, scene, "-L", "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "net.ppm")], capture_output=True, timeout=300)
         assert net.returncode == 0, net.stderr.decode()
         assert b"Threads: 2" in net.stdout
         assert proc.wait(30) == 0
@@ -134,3 +134,24 @@ def test_sharded_worker_paths_render_the_same_pixels(tmp_path):
         if proc.poll() is None:
             proc.kill()
     assert (tmp_path / "net.ppm").read_bytes() == (tmp_path / "one.ppm").read_bytes()
+
+
+def test_local_gpus_and_a_node_share_one_job(tmp_path):
+    """Without -L the manager's own GPUs pull work units from the same queue as the node (LocalWorker beside
+    NetworkWorker in the reference).  Same seed everywhere, so the frame is the local render's, whoever rendered
+    which unit; both must have rendered some."""
+    cli = os.path.join(ROOT, "host", "fluxb200")
+    scene = os.path.join(ROOT, "scenes", "demo2.yml")
+    common = ["-r", "16", "-R", "5", "--width", "96", "--height", "80", "--seed", "6"]
+    proc, port = start_node("--seed", "6")
+    try:
+        both = subprocess.run([cli, scene, "-n", f"127.0.0.1:{port}", *common, "-o", str(tmp_path / "both.ppm")], capture_output=True, timeout=300)
+        assert both.returncode == 0, both.stderr.decode()
+        assert proc.wait(30) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+    assert both.stdout.count(b"ready, info:") == 2
+    local = subprocess.run([cli, scene, *common, "-o", str(tmp_path / "local.ppm")], capture_output=True, timeout=300)
+    assert local.returncode == 0, local.stderr.decode()
+    assert (tmp_path / "both.ppm").read_bytes() == (tmp_path / "local.ppm").read_bytes()

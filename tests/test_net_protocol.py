@@ -295,7 +295,7 @@ def test_cpp_network_worker_drives_a_node(node, tmp_path, form):
     from flux_b200 import _capi
     fake = FakeNode()
     out = tmp_path / "net.ppm"
-    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-n", f"127.0.0.1:{fake.port}",
+    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-L", "-n", f"127.0.0.1:{fake.port}",
                         "-r", "3", "-d", "4", "-R", "7", "--width", "24", "--height", "20", "--seed", "99", "-o", str(out),
                         "--enum-form", form],
                        capture_output=True, timeout=120)
@@ -335,7 +335,7 @@ def test_cpp_manager_shares_one_job_between_two_nodes(node, tmp_path):
     fakes = [FakeNode(num_threads=2), FakeNode(num_threads=7)]
     out = tmp_path / "two.ppm"
     p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"),
-                        "-n", f"127.0.0.1:{fakes[0].port}", "-n", f"127.0.0.1:{fakes[1].port}",
+                        "-L", "-n", f"127.0.0.1:{fakes[0].port}", "-n", f"127.0.0.1:{fakes[1].port}",
                         "-r", "2", "-R", "3", "--width", "24", "--height", "31", "--seed", "4", "-o", str(out)],
                        capture_output=True, timeout=120)
     for f in fakes:
@@ -371,8 +371,20 @@ def test_cpp_manager_reports_a_node_that_goes_away(node, tmp_path):
     t = threading.Thread(target=rude, daemon=True)
     t.start()
     out = tmp_path / "gone.ppm"
-    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-n", f"127.0.0.1:{srv.getsockname()[1]}",
+    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-L", "-n", f"127.0.0.1:{srv.getsockname()[1]}",
                         "--width", "8", "--height", "8", "-o", str(out)], capture_output=True, timeout=120)
     t.join(10)
     assert p.returncode == 101 and (b"closed the connection" in p.stderr or b"send:" in p.stderr or b"recv:" in p.stderr), p.stderr
     assert not out.exists()
+
+
+def test_manager_without_dash_L_needs_a_gpu(node, tmp_path):
+    """Without -L the GPUs of the manager's box render beside the nodes (the reference's local worker,
+    flux/src/main.rs:43-60); on a box without a GPU that fails loudly instead of falling back to anything."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fake = FakeNode()
+    p = subprocess.run([os.path.join(ROOT, "host", "fluxb200"), os.path.join(ROOT, "scenes", "demo1.yml"), "-n", f"127.0.0.1:{fake.port}",
+                        "--width", "8", "--height", "8", "-o", str(tmp_path / "x.ppm")], capture_output=True, timeout=120)
+    assert p.returncode == 101 and b"flux_ctx_create" in p.stderr
