@@ -6,6 +6,7 @@ import pytest
 
 from flux_b200 import (CameraData, CameraSettings, Emissive, JobConfiguration, Matte, OutputSettings, PlaneData, Reflective,
                        SceneData, SphereData)
+from flux_b200.worker import FluxError
 from oracle import oracle_py as O
 from tests import helpers as Hp
 
@@ -139,3 +140,47 @@ def test_largest_image_through_size_independent_properties(gpu_ctx):
     ss_o.set_index = O.generate_set_index(11, h, w, w)
     ref = O.render_rows(sd.flatten(), cfg, ss_o, 1152, 1153)
     assert Hp.rel_err(full[1152:1154], ref) <= 1e-12
+
+
+def test_triangles_only_many_planes_and_120_spheres(gpu_ctx):
+    """Shape mixes at the edges of the kernel-selection rules: no sphere at all (triangles only: the BVH's linear
+    list is empty), forty planes (every one is tested by every ray), and 120 spheres (beyond the 112 the wavefront
+    kernel scans linearly: its BVH owner stage)."""
+    from flux_b200 import BoxData, RectangleData
+    rng = np.random.default_rng(12)
+    light = Emissive((1.0, 0.95, 0.9), 4.0)
+    grey = Matte((0.6, 0.6, 0.6), (1, 1, 1), 1.0)
+    tri_only = _scene([RectangleData((-6, 0, -6), (0, 0, 12), (12, 0, 0), grey), RectangleData((-2, 4, -2), (4, 0, 0), (0, 0, 4), light),
+                       BoxData((-1.0, 0.0, -0.5), (0.5, 1.5, 1.0), Reflective(0.8, (0.9, 0.9, 0.9)))], 20, 14)
+    planes = [PlaneData(tuple(map(float, rng.uniform(-6, 6, 3))), tuple(map(float, rng.standard_normal(3))),
+                        Matte(tuple(map(float, rng.uniform(0.3, 0.9, 3))), (1, 1, 1), 1.0)) for _ in range(39)]
+    many_planes = _scene(planes + [PlaneData((0, 9, 0), (0, -1, 0), light)], 20, 14)
+    spheres = [SphereData((0, 0, 0), 60.0, Emissive((1, 1, 1), 0.4), True)]
+    spheres += [SphereData(tuple(map(float, rng.uniform(-5, 5, 3))), float(rng.uniform(0.2, 0.7)),
+                           Matte(tuple(map(float, rng.uniform(0.3, 0.9, 3))), (1, 1, 1), 1.0) if k % 2 else Reflective(0.8, (0.9, 0.9, 0.9)), False)
+                for k in range(119)]
+    crowd = _scene(spheres, 20, 14)
+    cfg = JobConfiguration(16, 5, 50)
+    taken = []
+    for sd in (tri_only, many_planes, crowd):
+        w, h = sd.output_settings.image_width, sd.output_settings.image_height
+        flat = sd.flatten()
+        ss = Hp.oracle_samples(9, cfg, w, h)
+        ref = O.render_rows(flat, cfg, ss, 0, h - 1)
+        Hp.upload(gpu_ctx, flat, cfg, ss)
+        try:
+            imgs = {}
+            for mode in (0, 1, 2, 4):
+                gpu_ctx.set_kernel_mode(mode)
+                try:
+                    imgs[mode] = gpu_ctx.render_rows(0, h - 1, w)
+                except FluxError as e:      # a forced kernel that does not take this scene says so; auto and direct always do
+                    assert mode in (2, 4) and "needs" in str(e), (len(sd.shapes), mode, str(e))
+                    continue
+                assert Hp.rel_err(imgs[mode], ref) <= 1e-12, (len(sd.shapes), mode)
+            assert 0 in imgs and 1 in imgs
+            taken.append(sorted(imgs))
+        finally:
+            gpu_ctx.set_kernel_mode(0)
+    # a few triangles without a BVH leave only the direct kernel; the 120-sphere scene (BVH) is taken by every kernel
+    assert taken[0] == [0, 1] and taken[2] == [0, 1, 2, 4], taken
