@@ -328,6 +328,72 @@ class SceneData:  # scene.rs:42-49
     def from_yaml_string(text: str) -> "SceneData":
         return SceneData.from_dict(yaml.safe_load(text))
 
+    # -- the way back: a scene file serde_yaml (and both loaders here) reads; doubles survive exactly --
+    def to_yaml(self, path: str) -> None:
+        """Writes the scene as YAML in the reference's format (externally tagged enums, 3-sequences for vectors and
+        colours; the extension shapes under their own tags).  Floats are written with repr() and always carry a
+        '.', so YAML 1.1 and 1.2 readers both take them as floats and get the same double back."""
+        def f(x):
+            x = float(x)
+            if x != x:
+                return ".nan"
+            if x in (float("inf"), float("-inf")):
+                return ".inf" if x > 0 else "-.inf"
+            r = repr(x)
+            if "e" in r and "." not in r.split("e")[0]:
+                m, e = r.split("e")
+                r = m + ".0e" + e
+            return r
+
+        def v(p):
+            return "[" + ", ".join(f(c) for c in p) + "]"
+
+        def mat(m):
+            if isinstance(m, Matte):
+                return (f"Matte: {{diffuse_color: {v(m.diffuse_color)}, ambient_color: {v(m.ambient_color)}, "
+                        f"diffuse_coefficient: {f(m.diffuse_coefficient)}}}")
+            if isinstance(m, Emissive):
+                return f"Emissive: {{color: {v(m.color)}, power: {f(m.power)}}}"
+            if isinstance(m, Reflective):
+                return f"Reflective: {{reflect_amount: {f(m.reflect_amount)}, reflect_color: {v(m.reflect_color)}}}"
+            return (f"GlossyReflective: {{reflect_amount: {f(m.reflect_amount)}, reflect_color: {v(m.reflect_color)}, "
+                    f"reflect_exponent: {f(m.reflect_exponent)}}}")
+
+        import json
+        o, cs, cd = self.output_settings, self.camera_settings, self.camera_data
+        with open(path, "w") as out:
+            w = out.write
+            w(f"scene_name: {json.dumps(self.scene_name)}\n")
+            w(f"camera_settings:\n  eye: {v(cs.eye)}\n  look_at: {v(cs.look_at)}\n  up: {v(cs.up)}\n")
+            w(f"camera_data:\n  zoom_factor: {f(cd.zoom_factor)}\n  view_plane_distance: {f(cd.view_plane_distance)}\n"
+              f"  focal_distance: {f(cd.focal_distance)}\n  lens_radius: {f(cd.lens_radius)}\n")
+            w(f"output_settings:\n  image_width: {int(o.image_width)}\n  image_height: {int(o.image_height)}\n"
+              f"  pixel_size: {f(o.pixel_size)}\n")
+            w(f"background: {v(self.background)}\nshapes:\n")
+            for sh in self.shapes:
+                if isinstance(sh, SphereData):
+                    w(f"- Sphere:\n    center: {v(sh.center)}\n    radius: {f(sh.radius)}\n    material:\n      {mat(sh.material)}\n"
+                      f"    invert: {'true' if sh.invert else 'false'}\n")
+                elif isinstance(sh, PlaneData):
+                    w(f"- Plane:\n    point: {v(sh.point)}\n    normal: {v(sh.normal)}\n    material:\n      {mat(sh.material)}\n")
+                elif isinstance(sh, TriangleData):
+                    w(f"- Triangle:\n    v0: {v(sh.v0)}\n    v1: {v(sh.v1)}\n    v2: {v(sh.v2)}\n    material:\n      {mat(sh.material)}\n")
+                elif isinstance(sh, RectangleData):
+                    w(f"- Rectangle:\n    corner: {v(sh.corner)}\n    edge_a: {v(sh.edge_a)}\n    edge_b: {v(sh.edge_b)}\n"
+                      f"    material:\n      {mat(sh.material)}\n")
+                elif isinstance(sh, BoxData):
+                    w(f"- Box:\n    min: {v(sh.min)}\n    max: {v(sh.max)}\n    material:\n      {mat(sh.material)}\n")
+                elif isinstance(sh, MeshData):
+                    w("- Mesh:\n    vertices:\n")
+                    for p in np.asarray(sh.vertices, np.float64):
+                        w(f"      - {v(p)}\n")
+                    w("    faces:\n")
+                    for t in np.asarray(sh.faces, np.int64):
+                        w(f"      - [{int(t[0])}, {int(t[1])}, {int(t[2])}]\n")
+                    w(f"    material:\n      {mat(sh.material)}\n")
+                else:
+                    raise TypeError(f"not a ShapeData: {sh!r}")
+
     def with_size(self, width: int, height: int) -> "SceneData":
         """Same scene at another resolution (BASELINE config 1: demo1 at 512x512;
         the reference has no CLI override)."""

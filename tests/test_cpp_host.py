@@ -192,3 +192,32 @@ def test_cli_renders_the_same_ppm_as_the_python_mirror(fluxb200, tmp_path):
     assert _capi.lib().flux_write_ppm(str(ref).encode(), 64, 48, img.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
     assert out.read_bytes() == ref.read_bytes()
     assert out.read_text().startswith("P3\n64 48\n65535\n")
+
+
+def _scenes_to_write():
+    from flux_b200 import (CameraData, CameraSettings, Emissive, Matte, OutputSettings, PlaneData, SphereData, synth)
+    from tests import helpers as Hp
+    from tests.test_extension_shapes import room_scene
+    yield "deterministic", Hp.deterministic_scene()
+    yield "room", room_scene()                                            # rectangles, boxes
+    yield "glossy", synth.glossy_scene()                                   # config 4: all material kinds
+    yield "mesh", synth.mesh_scene(200, 100, seed=3, width=40, height=30)  # config 3 at 1/25 size: 40 000 triangles
+    odd = [SphereData((5e-324, -0.0, 1e300), 2.2250738585072014e-308, Emissive((float("inf"), 0.1, 1 / 3), 1e-5), True),
+           PlaneData((1e21, -1e-7, 123456789.125), (0.0, 1.0, float("nan")), Matte((0.1, 0.2, 0.3), (1, 1, 1), 1.0))]
+    yield "odd floats", SceneData('name with "quotes" and: colons', OutputSettings(3, 2, 0.5), (0.0, 0.0, 0.0), odd,
+                                  CameraSettings((0, 0, -5), (0, 0, 0), (0, 1, 0)), CameraData(1.0, 500.0, 10.0, 0.0))
+
+
+@pytest.mark.parametrize("name,sd", list(_scenes_to_write()), ids=[n for n, _ in _scenes_to_write()])
+def test_written_scene_files_load_back_exactly_in_both_loaders(fluxb200, tmp_path, name, sd):
+    """SceneData.to_yaml writes what serde_yaml reads; the Python loader and the C++ loader get every double back
+    bit for bit (NaN, infinities, -0.0, denormals and exponents without a fraction included)."""
+    path = tmp_path / "scene.yml"
+    sd.to_yaml(str(path))
+    back = SceneData.from_yaml(str(path))
+    assert back.scene_name == sd.scene_name and len(back.shapes) == len(sd.shapes)
+    out = tmp_path / "flat.txt"
+    subprocess.run([fluxb200, str(path), "--dump-flat", str(out)], check=True)
+    d = _parse_dump(out)
+    _check_same(d, sd)        # C++ loader of the written file == the original scene, flattened
+    _check_same(d, back)      # ... == the Python loader of the written file
