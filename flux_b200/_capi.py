@@ -86,6 +86,7 @@ PROTOTYPES = {
     "flux_launch_count": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
     "flux_set_accel_mode": (C.c_int, [_ctx, C.c_int]),
     "flux_bvh_describe": (C.c_int, [C.POINTER(flux_scene_flat), C.POINTER(C.c_uint64)]),
+    "flux_bvh_hash": (C.c_int, [C.POINTER(flux_scene_flat), C.POINTER(C.c_uint64)]),
     "flux_set_kernel_mode": (C.c_int, [_ctx, C.c_int]),
     "flux_set_glossy_table": (C.c_int, [_ctx, C.c_int]),
     "flux_measure_fp64_peak": (C.c_int, [_ctx, _dp]),

