@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
+#include <mutex>
 #include <limits>
 #include <string>
 #include <thread>
@@ -120,7 +122,7 @@ struct Builder {
         }
     }
     // builds the subtree over [a,b) (b - a > leaf_size) and returns its node index; level = depth of this node
-    uint32_t build_node(uint32_t a, uint32_t b, uint32_t level) {
+    uint32_t build_node(uint32_t a, uint32_t b, uint32_t level, Box *whole = nullptr) {
         const uint32_t me = (uint32_t)out->nodes.size();
         out->nodes.emplace_back();
         out->depth = std::max(out->depth, level + 1);
@@ -142,13 +144,25 @@ struct Builder {
         cut[1] = (cut[2] - a > leaf_size) ? split(a, cut[2]) : a;          // a == "no split": slot 0 empty
         cut[3] = (b - cut[2] > leaf_size) ? split(cut[2], b) : cut[2];
         int slot = 0;
+        Box mine;
+        mine.reset();
         for (int q = 0; q < 4; q++) {
             const uint32_t qa = cut[q], qb = cut[q + 1];
             if (qa == qb) continue;
-            const Box bx = bounds(qa, qb);
-            const uint32_t ref = (qb - qa <= leaf_size) ? make_leaf(qa, qb) : build_node(qa, qb, level + 1);
+            // the box of a subtree is the union of its children's boxes (min / max are exact, so this is the very
+            // box a scan over its items gives): one pass over the items in all, not one per level
+            Box bx;
+            uint32_t ref;
+            if (qb - qa <= leaf_size) {
+                bx = bounds(qa, qb);
+                ref = make_leaf(qa, qb);
+            } else {
+                ref = build_node(qa, qb, level + 1, &bx);
+            }
+            mine.grow(bx);
             set_child(me, slot++, ref, bx);
         }
+        if (whole) *whole = mine;
         return me;
     }
 };
@@ -183,7 +197,22 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         s.shape_id = sph_meta[i]; s.material = sph_meta[ns + i]; s.index = i; s.pad = 0;
     }
     out.tri.resize(nt);
-    for (uint32_t i = 0; i < nt; i++) {
+    // independent per triangle: in slices on several host threads when there are many
+    auto in_slices = [](uint32_t count, const std::function<void(uint32_t, uint32_t)> &body) {
+        const uint32_t nthreads = count >= (1u << 16) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+        if (nthreads == 1) {
+            body(0, count);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < nthreads; t++) {
+            const uint32_t lo = (uint32_t)((uint64_t)count * t / nthreads), hi = (uint32_t)((uint64_t)count * (t + 1) / nthreads);
+            th.emplace_back(body, lo, hi);
+        }
+        for (auto &x : th) x.join();
+    };
+    in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
+    for (uint32_t i = lo_i; i < hi_i; i++) {
         TriRec &q = out.tri[i];
         q.v0x = tri[(size_t)TRI_V0X * nt + i]; q.v0y = tri[(size_t)TRI_V0Y * nt + i]; q.v0z = tri[(size_t)TRI_V0Z * nt + i];
         q.e1x = tri[(size_t)TRI_E1X * nt + i]; q.e1y = tri[(size_t)TRI_E1Y * nt + i]; q.e1z = tri[(size_t)TRI_E1Z * nt + i];
@@ -191,6 +220,7 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         q.shape_id = tri_meta[i]; q.material = tri_meta[nt + i]; q.index = i;
         q.pad[0] = q.pad[1] = q.pad[2] = 0;
     }
+    });
     lap("records");
     // ---- primitive boxes ----
     Builder B;
@@ -217,7 +247,12 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         for (int k = 0; k < 3; k++) it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
         B.items.push_back(it);
     }
-    for (uint32_t i = 0; i < nt; i++) {
+    const size_t tri_base = B.items.size();
+    B.items.resize(tri_base + nt);
+    std::vector<uint32_t> first_bad(1, 0xFFFFFFFFu);
+    std::mutex bad_mu;
+    in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
+    for (uint32_t i = lo_i; i < hi_i; i++) {
         Item it;
         const TriRec &q = out.tri[i];
         const double v0[3] = {q.v0x, q.v0y, q.v0z};
@@ -230,11 +265,19 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
             it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
         }
         it.ref = ((uint32_t)KIND_TRI << 30) | i;
-        if (!finite_box(it.box)) {
-            err = "bvh: triangle " + std::to_string(i) + " has a non-finite vertex";
-            return false;
+        bool finite = finite_box(it.box);
+        for (int k = 0; k < 3; k++)   // min / max skip a NaN or not depending on where it stands: look at the vertices themselves
+            finite = finite && std::isfinite(v0[k]) && std::isfinite(tri_v1[3 * (size_t)i + k]) && std::isfinite(tri_v2[3 * (size_t)i + k]);
+        if (!finite) {
+            std::lock_guard<std::mutex> g(bad_mu);
+            first_bad[0] = std::min(first_bad[0], i);   // the lowest index, whichever thread saw it
         }
-        B.items.push_back(it);
+        B.items[tri_base + i] = it;
+    }
+    });
+    if (first_bad[0] != 0xFFFFFFFFu) {
+        err = "bvh: triangle " + std::to_string(first_bad[0]) + " has a non-finite vertex";
+        return false;
     }
     lap("boxes");
     // ---- oversized spheres go to the linear list (at most 64, largest first) ----

@@ -189,3 +189,19 @@ def test_bvh_builder_is_deterministic_and_plans_its_depth():
     assert _capi.lib().flux_bvh_describe(C.byref(s), d) == 0
     nodes, levels, leaf, linear, prims, violations, miscounted, used = list(d)
     assert (levels, leaf, prims, violations, miscounted) == (10, 4, n, 0, 0)
+
+
+def test_bvh_builder_names_the_first_triangle_with_a_non_finite_vertex():
+    """NaN and infinite vertices are refused by the builder (a triangle the linear scan can never hit has no box to
+    put in a tree), and the message names the lowest such triangle whichever host thread met it."""
+    import ctypes as C
+    from flux_b200 import _capi, synth
+    from flux_b200 import Matte, SceneData, TriangleData
+    sd = synth.mesh_scene(300, 200, seed=3)           # 120 000 triangles: the boxes are made in slices on several threads
+    m = Matte((0.5, 0.5, 0.5), (1, 1, 1), 1.0)
+    bad = [TriangleData((0, 0, 0), (1, float("nan"), 0), (0, 1, 0), m), TriangleData((0, 0, 0), (1, float("inf"), 0), (0, 1, 0), m)]
+    out = (C.c_uint64 * 8)()
+    for extra, first in ((bad, 120000), (bad[::-1], 120000), (bad[1:], 120000)):
+        flat = SceneData("bad", sd.output_settings, sd.background, list(sd.shapes) + extra, sd.camera_settings, sd.camera_data).flatten()
+        assert _capi.lib().flux_bvh_describe(flat.ptr(), out) != 0
+        assert _capi.lib().flux_last_error(None).decode() == f"bvh: triangle {first} has a non-finite vertex"
