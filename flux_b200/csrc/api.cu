@@ -51,6 +51,9 @@ struct flux_ctx {
     std::string err;
 
     bool have_scene = false, have_samples = false, have_index = false;
+    // what the set-index map on the device was validated (flux_set_set_index) or generated for: it is usable only
+    // while the image size and the number of sample sets are still these (index_valid)
+    uint32_t idx_W = 0, idx_H = 0, idx_sets = 0;
     flux_job_config cfg{};
     DevCamera cam{};
     DevScene scene{};
@@ -82,6 +85,24 @@ struct flux_ctx {
     uint32_t bvh_depth = 0, bvh_leaf = 0;
     float cull[FLUX_CULL_MAX][4];   // f32 spheres for render_wave2.cu (RenderParams::cull)
     float cull_cmax = 0.f;
+
+    bool index_valid() const {
+        return have_index && have_scene && have_samples && idx_W == cam.W && idx_H == cam.H && idx_sets == ss.num_sets;
+    }
+    // Called with the context's device current (flux_ctx_destroy, and the failure paths of flux_ctx_create).
+    ~flux_ctx() {
+        if (stream) cudaStreamSynchronize(stream);
+        sph.release(); pln.release(); tri.release(); hemi.release(); out.release(); ray_o.release(); ray_d.release();
+        ray_t.release(); sink.release(); ghemi.release(); ginv.release(); accum.release();
+        sph_meta.release(); pln_meta.release(); tri_meta.release(); set_index.release(); rows.release();
+        ray_hit.release(); materials.release(); pixel.release(); disc.release(); counters.release();
+        work_counter.release(); bvh_nodes.release(); bvh_sph.release(); bvh_tri.release(); bvh_prims.release();
+        bvh_linear.release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+    }
 };
 
 namespace {
@@ -205,7 +226,6 @@ int flux_ctx_create(int device, flux_ctx **out) {
     if (prop.major < 10) {
         g_create_error = "flux_ctx_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
                          "; libfluxb200 is built for sm_100a only";
-        cudaStreamDestroy(ctx->stream);
         delete ctx;
         return FLUX_ERR_NO_DEVICE;
     }
@@ -224,20 +244,8 @@ int flux_ctx_create(int device, flux_ctx **out) {
 
 int flux_ctx_destroy(flux_ctx *ctx) {
     if (!ctx) return FLUX_ERR_INVALID;
-    {
-        DeviceGuard g(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        ctx->sph.release(); ctx->pln.release(); ctx->tri.release(); ctx->hemi.release(); ctx->out.release();
-        ctx->ray_o.release(); ctx->ray_d.release(); ctx->ray_t.release(); ctx->sink.release();
-        ctx->sph_meta.release(); ctx->pln_meta.release(); ctx->tri_meta.release(); ctx->set_index.release();
-        ctx->rows.release(); ctx->ray_hit.release(); ctx->materials.release(); ctx->pixel.release();
-        ctx->disc.release(); ctx->counters.release(); ctx->work_counter.release(); ctx->ghemi.release(); ctx->ginv.release();
-        ctx->bvh_nodes.release(); ctx->bvh_sph.release(); ctx->bvh_tri.release(); ctx->bvh_prims.release(); ctx->bvh_linear.release();
-        cudaEventDestroy(ctx->ev0);
-        cudaEventDestroy(ctx->ev1);
-        cudaStreamDestroy(ctx->stream);
-    }
-    delete ctx;
+    DeviceGuard g(ctx->device);
+    delete ctx;   // ~flux_ctx releases every device buffer (the progressive accumulator included), events and the stream
     return FLUX_OK;
 }
 
@@ -273,6 +281,14 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         return FLUX_ERR_INVALID;
     for (uint32_t i = 0; i < s->n_materials; i++)
         if (s->materials[i].kind > FLUX_MAT_GLOSSY) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: unknown material kind");
+    // Triangles are this library's extension and their vertices must be finite — whichever way the closest hit is then
+    // found, so that adding an unrelated shape (and with it the BVH, whose builder has no box for such a triangle)
+    // never turns a scene that rendered into an error.  Spheres and planes keep the reference's semantics: anything goes.
+    for (uint32_t i = 0; i < s->n_triangles; i++)
+        for (int k = 0; k < 3; k++)
+            if (!std::isfinite(s->tri_v0[3 * (size_t)i + k]) || !std::isfinite(s->tri_v1[3 * (size_t)i + k]) ||
+                !std::isfinite(s->tri_v2[3 * (size_t)i + k]))
+                return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: triangle " + std::to_string(i) + " has a non-finite vertex");
 
     DeviceGuard g(ctx->device);
     ctx->have_scene = false;
@@ -433,8 +449,9 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     // samples / set index belong to a job: a new scene invalidates them if shapes changed
     if (ctx->have_samples && (ctx->ss.root != cfg->sample_root || ctx->ss.max_depth != cfg->max_trace_depth))
         ctx->have_samples = false;
-        ctx->prog_active = false;
-    if (ctx->have_index && ctx->set_index.cap < (size_t)cam.W * cam.H) ctx->have_index = false;
+    // the set-index map is [H][W] of set numbers: another image size (even one that fits the old allocation) or
+    // fewer sample sets make it stale
+    if (ctx->have_index && (ctx->idx_W != cam.W || ctx->idx_H != cam.H || !ctx->have_samples)) ctx->have_index = false;
     if (ctx->have_samples) return build_glossy_table(ctx);  // exponents may have changed
     ctx->ss.ghemi = nullptr;
     ctx->ss.gk = 0;
@@ -490,6 +507,8 @@ int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t 
     DeviceGuard g(ctx->device);
     ctx->have_samples = false;
     ctx->prog_active = false;
+    // a map validated against another number of sets (or another image) may name sets that no longer exist
+    if (ctx->have_index && (ctx->idx_sets != num_sets || ctx->idx_W != ctx->cam.W || ctx->idx_H != ctx->cam.H)) ctx->have_index = false;
     int rc = alloc_samples(ctx, root, max_depth, num_sets);
     if (rc) return rc;
     const size_t n = (size_t)root * root;
@@ -527,6 +546,7 @@ int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->have_samples = true;
     ctx->have_index = true;
+    ctx->idx_W = ctx->cam.W; ctx->idx_H = ctx->cam.H; ctx->idx_sets = num_sets;
     return build_glossy_table(ctx);
 }
 
@@ -545,7 +565,7 @@ int flux_get_samples(flux_ctx *ctx, double *pixel_xy, double *disc_xy, double *h
 
 int flux_get_set_index(flux_ctx *ctx, uint32_t *idx) {
     if (!ctx) return FLUX_ERR_INVALID;
-    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "flux_get_set_index: no set-index map on the device");
+    if (!ctx->index_valid()) return fail(ctx, FLUX_ERR_STATE, "flux_get_set_index: no set-index map on the device");
     if (!idx) return fail(ctx, FLUX_ERR_INVALID, "flux_get_set_index: null output");
     DeviceGuard g(ctx->device);
     CK(cudaMemcpyAsync(idx, ctx->set_index.p, (size_t)ctx->cam.W * ctx->cam.H * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -567,6 +587,7 @@ int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx) {
     CK(cudaMemcpyAsync(ctx->set_index.p, idx, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_index = true;
+    ctx->idx_W = ctx->cam.W; ctx->idx_H = ctx->cam.H; ctx->idx_sets = ctx->ss.num_sets;
     return FLUX_OK;
 }
 
@@ -587,7 +608,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
                          bool sync_to_user) {
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "render: scene not set");
     if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
-    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set");
+    if (!ctx->index_valid()) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set (or set for another image size / number of sample sets)");
     if (n_rows == 0) return FLUX_OK;
     if (!rows || !d_out) return fail(ctx, FLUX_ERR_INVALID, "render: null rows or output");
     for (uint32_t k = 0; k < n_rows; k++) {
@@ -703,7 +724,7 @@ int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->prog_active) return fail(ctx, FLUX_ERR_STATE, "progressive: flux_progressive_begin not called (or the scene changed since)");
     if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
-    if (!ctx->have_index) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set");
+    if (!ctx->index_valid()) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set (or set for another image size / number of sample sets)");
     if (sample_begin != ctx->prog_done) return fail(ctx, FLUX_ERR_INVALID, "progressive: passes must continue where the last one ended");
     if (sample_end <= sample_begin || sample_end > ctx->ss.n) return fail(ctx, FLUX_ERR_INVALID, "progressive: bad sample range");
     const uint32_t n_rows = (uint32_t)ctx->prog_rows.size();

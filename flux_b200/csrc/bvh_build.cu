@@ -12,11 +12,23 @@
 #include <mutex>
 #include <limits>
 #include <string>
+#include <system_error>
 #include <thread>
 
 #include "flux_bvh.cuh"
 
 namespace {
+
+// A host thread when one can be had, else the work inline: std::thread's constructor throws std::system_error when the
+// process is out of threads, and an exception must not leave a joinable thread behind or cross the C ABI.  The tree
+// does not depend on which of the two happened (partition() below).
+template <class F> void spawn_or_run(std::vector<std::thread> &pool, F f) {
+    try {
+        pool.emplace_back(f);
+    } catch (const std::system_error &) {
+        f();
+    }
+}
 
 struct Box {
     double lo[3], hi[3];
@@ -68,9 +80,10 @@ struct Builder {
         auto right = [&] { cut[3] = (b - cut[2] > leaf_size) ? split(cut[2], b) : cut[2]; };
         const bool par = par_levels > 0 && b - a >= (1u << 15);
         if (par) {
-            std::thread t(left);
+            std::vector<std::thread> one;
+            spawn_or_run(one, left);
             right();
-            t.join();
+            for (auto &t : one) t.join();
         } else {
             left();
             right();
@@ -79,7 +92,7 @@ struct Builder {
         for (int q = 0; q < 4; q++) {
             const uint32_t qa = cut[q], qb = cut[q + 1];
             if (qb - qa <= leaf_size) continue;
-            if (par && q < 3) th.emplace_back([this, qa, qb, par_levels] { partition(qa, qb, par_levels - 1); });
+            if (par && q < 3) spawn_or_run(th, [this, qa, qb, par_levels] { partition(qa, qb, par_levels - 1); });
             else partition(qa, qb, par ? par_levels - 1 : 0);
         }
         for (auto &t : th) t.join();
@@ -169,8 +182,25 @@ struct Builder {
 
 }  // namespace
 
+static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
+                            const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err);
+
+// No exception leaves the builder: its callers are extern "C" (flux_set_scene, flux_bvh_describe, flux_bvh_hash).
 bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
                 const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err) {
+    try {
+        return build_bvh4_impl(sph, sph_meta, ns, tri, tri_meta, tri_v1, tri_v2, nt, out, err);
+    } catch (const std::exception &e) {
+        err = std::string("bvh: ") + e.what();
+    } catch (...) {
+        err = "bvh: unknown failure";
+    }
+    out = BvhBuild{};
+    return false;
+}
+
+static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_t ns, const double *tri, const uint32_t *tri_meta,
+                            const double *tri_v1, const double *tri_v2, uint32_t nt, BvhBuild &out, std::string &err) {
     out = BvhBuild{};
     const bool timing = std::getenv("FLUX_BVH_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -207,7 +237,7 @@ bool build_bvh4(const double *sph, const uint32_t *sph_meta, uint32_t ns, const 
         std::vector<std::thread> th;
         for (uint32_t t = 0; t < nthreads; t++) {
             const uint32_t lo = (uint32_t)((uint64_t)count * t / nthreads), hi = (uint32_t)((uint64_t)count * (t + 1) / nthreads);
-            th.emplace_back(body, lo, hi);
+            spawn_or_run(th, [&body, lo, hi] { body(lo, hi); });
         }
         for (auto &x : th) x.join();
     };

@@ -11,7 +11,11 @@ using detail::Node;
 
 namespace {
 constexpr int MAX_DEPTH = 64;
-constexpr uint64_t MAX_ITEMS = 1ull << 28;        // a 16 K x 16 K frame of colours is 1 G items; a work unit is far less
+// Every item becomes a detail::Node (~100 bytes with its string, vector and map), so the item budget is a memory
+// budget: 2^26 items bound one message at a few GB where 2^28 let a 256 MB message of one-byte items ask for tens of GB
+// (ADVICE r1).  The largest legitimate messages: SetJob with a million-triangle mesh, ~1.5e7 items; RowsReady of a
+// 50-row unit at 16 K pixels per row, 3.3e6.
+constexpr uint64_t MAX_ITEMS = 1ull << 26;
 constexpr uint64_t MAX_STRING = 1ull << 28;
 
 double half_to_double(uint16_t h) {

@@ -184,3 +184,41 @@ def test_triangles_only_many_planes_and_120_spheres(gpu_ctx):
             gpu_ctx.set_kernel_mode(0)
     # a few triangles without a BVH leave only the direct kernel; the 120-sphere scene (BVH) is taken by every kernel
     assert taken[0] == [0, 1] and taken[2] == [0, 1, 2, 4], taken
+
+
+def test_stale_set_index_map_is_refused(gpu_ctx):
+    """A set-index map names sample sets: it must not outlive the image size or the number of sets it was checked
+    against.  set_scene(root 2) + 800 sets + map, then set_scene(root 8) + 4 sets + render used to read sets 4..799
+    of allocations that hold 4; it is a call-order error now."""
+    shapes = [SphereData((0, 0, 0), 100.0, Emissive((1, 0.9, 0.8), 0.6), True)]
+    sd = _scene(shapes, 40, 30)
+    flat = sd.flatten()
+    cfg2, cfg8 = JobConfiguration(2, 5, 50), JobConfiguration(8, 5, 50)
+    ss2 = Hp.oracle_samples(1, cfg2, 40, 30, num_sets=800)
+    assert ss2.set_index.max() >= 4
+    Hp.upload(gpu_ctx, flat, cfg2, ss2)
+    gpu_ctx.render_rows(0, 29, 40)
+    gpu_ctx.set_scene(flat, cfg8)
+    ss8 = Hp.oracle_samples(1, cfg8, 40, 30, num_sets=4)
+    gpu_ctx.set_samples(ss8.root, ss8.max_depth, 4, ss8.pixel, ss8.disc, ss8.hemi)
+    with pytest.raises(FluxError) as e:
+        gpu_ctx.render_rows(0, 29, 40)
+    assert e.value.code == 3   # FLUX_ERR_STATE
+    # same root, fewer sets: the map is stale as well
+    Hp.upload(gpu_ctx, flat, cfg2, ss2)
+    ss2b = Hp.oracle_samples(1, cfg2, 40, 30, num_sets=4)
+    gpu_ctx.set_samples(2, 5, 4, ss2b.pixel, ss2b.disc, ss2b.hemi)
+    with pytest.raises(FluxError) as e:
+        gpu_ctx.render_rows(0, 29, 40)
+    assert e.value.code == 3
+    # another image size that still fits the old allocation
+    Hp.upload(gpu_ctx, flat, cfg2, ss2)
+    small = _scene(shapes, 20, 10).flatten()
+    gpu_ctx.set_scene(small, cfg2)
+    with pytest.raises(FluxError) as e:
+        gpu_ctx.render_rows(0, 9, 20)
+    assert e.value.code == 3
+    # and the proper sequence still renders
+    gpu_ctx.set_set_index(np.zeros((10, 20), np.uint32))
+    img = gpu_ctx.render_rows(0, 9, 20)
+    assert np.isfinite(img).all()
