@@ -93,7 +93,18 @@ PROTOTYPES = {
     "flux_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _dp]),
     "flux_progressive_begin": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_uint32]),
     "flux_progressive_pass": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, _dp]),
+    # multi-GPU frame assembly over peer memory
+    "flux_frame_create": (C.c_int, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "flux_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flux_frame_open_ipc": (C.c_int, [_ctx, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "flux_frame_open_peer": (C.c_int, [_ctx, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "flux_render_row_list_into_frame": (C.c_int, [_ctx, _u32p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "flux_ctx_sync": (C.c_int, [_ctx]),
+    "flux_frame_read": (C.c_int, [C.c_void_p, _dp]),
+    "flux_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "flux_frame_close": (C.c_int, [C.c_void_p]),
 }
+FLUX_FRAME_HANDLE_BYTES = 64
 
 # FLUXB200_LIB selects an alternative build of the same library (A/B of compile-time kernel variants)
 LIB_PATH = os.environ.get("FLUXB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfluxb200.so")

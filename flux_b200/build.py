@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libfluxb200.so")
-SOURCES = ["api.cu", "bvh_build.cu", "render.cu", "render_regen.cu", "render_wave.cu", "render_wave2.cu", "samplegen.cu"]
+SOURCES = ["api.cu", "bvh_build.cu", "render.cu", "render_regen.cu", "render_wave2.cu", "samplegen.cu"]
 
 # -fmad=false: the Rust reference never contracts a*b+c; bit parity of hit distances and
 # radiance depends on it.  Host code: -ffp-contract=off for the same reason.

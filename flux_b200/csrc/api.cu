@@ -59,7 +59,7 @@ struct flux_ctx {
     DevScene scene{};
     DevSamples ss{};
     int accel_mode = 0;
-    int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu), 3 wavefront (render_wave.cu)
+    int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu), 4 wavefront (render_wave2.cu)
     bool count = false;
     float last_ms = 0.f;
     uint64_t launches = 0;
@@ -605,7 +605,7 @@ int flux_shard_rows(uint32_t image_height, uint32_t tile_rows, uint32_t rank, ui
 }
 
 static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *d_out, cudaStream_t user_stream,
-                         bool sync_to_user) {
+                         bool sync_to_user, bool out_by_row = false) {
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "render: scene not set");
     if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
     if (!ctx->index_valid()) return fail(ctx, FLUX_ERR_STATE, "render: set-index map not set (or set for another image size / number of sample sets)");
@@ -633,6 +633,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     p.rows = ctx->rows.p;
     p.n_rows = n_rows;
     p.out = d_out;
+    p.out_by_row = out_by_row ? 1u : 0u;
     p.counters = ctx->counters.p;
     p.work_counter = ctx->work_counter.p;
     std::memcpy(p.cull, ctx->cull, sizeof(p.cull));
@@ -644,9 +645,6 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     const bool regen_ok = regen_kernel_applicable(p);
     if (ctx->kernel_mode == 2 && !regen_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: regeneration kernel needs spp >= 64 and a BVH scene or a sphere/plane scene that fits shared memory");
-    const bool wave_ok = wave_kernel_applicable(p);
-    if (ctx->kernel_mode == 3 && !wave_ok)
-        return fail(ctx, FLUX_ERR_INVALID, "render: wavefront kernel needs spp >= 4096, depth <= 8 and a small sphere/plane scene");
     const bool wave2_ok = wave2_kernel_applicable(p);
     if (ctx->kernel_mode == 4 && !wave2_ok)
         return fail(ctx, FLUX_ERR_INVALID, "render: wavefront-2 kernel needs spp >= 256, depth <= 8 and a sphere/plane scene of at most 128 spheres");
@@ -665,8 +663,6 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
         launch_render_wave2(q, ctx->count, ctx->sm_count, st);
     else if ((wave2_auto && ctx->kernel_mode == 0) || (wave2_ok && ctx->kernel_mode == 4))
         launch_render_wave2(p, ctx->count, ctx->sm_count, st);
-    else if (wave_ok && (ctx->kernel_mode == 0 || ctx->kernel_mode == 3))
-        launch_render_wave(p, ctx->count, ctx->sm_count, st);
     else if (regen_ok && ctx->kernel_mode != 1)
         launch_render_regen(p, ctx->count, ctx->sm_count, st);
     else
@@ -696,6 +692,138 @@ int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     if (elems) CK(cudaMemcpyAsync(out_rgb, ctx->out.p, elems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_rows) CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return FLUX_OK;
+}
+
+// ---- multi-GPU frame assembly over peer memory (include/fluxb200.h) ----------------------------------------------
+}  // extern "C"
+
+struct flux_frame {
+    int device = 0;          // device the mapping belongs to (the caller's GPU, not necessarily the owner's)
+    double *p = nullptr;     // [H][W][3] on the owner's GPU
+    uint32_t W = 0, H = 0;
+    int kind = 0;            // 0 owner (cudaMalloc), 1 CUDA IPC mapping, 2 peer alias inside one process
+};
+
+extern "C" {
+
+int flux_frame_create(flux_ctx *ctx, uint32_t W, uint32_t H, flux_frame **out) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!out || W == 0 || H == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_create: bad arguments");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    flux_frame *f = new (std::nothrow) flux_frame();
+    if (!f) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_create: out of memory");
+    f->device = ctx->device; f->W = W; f->H = H; f->kind = 0;
+    const size_t bytes = (size_t)W * H * 3 * sizeof(double);
+    // plain cudaMalloc (not a pool, not VMM): the allocation must be exportable as a CUDA IPC handle
+    cudaError_t e = cudaMalloc((void **)&f->p, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->p, 0, bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (f->p) cudaFree(f->p);
+        delete f;
+        return fail(ctx, FLUX_ERR_CUDA, std::string("flux_frame_create: ") + cudaGetErrorString(e));
+    }
+    *out = f;
+    return FLUX_OK;
+}
+
+int flux_frame_export(flux_frame *f, unsigned char *handle) {
+    if (!f || !handle || f->kind != 0) return FLUX_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == FLUX_FRAME_HANDLE_BYTES, "CUDA IPC handle size");
+    DeviceGuard g(f->device);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, f->p) != cudaSuccess) {
+        g_create_error = std::string("flux_frame_export: ") + cudaGetErrorString(cudaGetLastError());
+        return FLUX_ERR_CUDA;
+    }
+    std::memcpy(handle, &h, sizeof h);
+    return FLUX_OK;
+}
+
+int flux_frame_open_ipc(flux_ctx *ctx, const unsigned char *handle, uint32_t W, uint32_t H, flux_frame **out) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!out || !handle || W == 0 || H == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_ipc: bad arguments");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    flux_frame *f = new (std::nothrow) flux_frame();
+    if (!f) {
+        cudaIpcCloseMemHandle(p);
+        return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_ipc: out of memory");
+    }
+    f->device = ctx->device; f->p = (double *)p; f->W = W; f->H = H; f->kind = 1;
+    *out = f;
+    return FLUX_OK;
+}
+
+int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner, flux_frame **out) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!out || !owner || owner->kind != 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_peer: bad arguments");
+    *out = nullptr;
+    DeviceGuard g(ctx->device);
+    if (owner->device != ctx->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, owner->device));
+        if (!can)
+            return fail(ctx, FLUX_ERR_CUDA, "flux_frame_open_peer: device " + std::to_string(ctx->device) +
+                                                " has no peer access to device " + std::to_string(owner->device));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(ctx, FLUX_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    flux_frame *f = new (std::nothrow) flux_frame();
+    if (!f) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_peer: out of memory");
+    f->device = ctx->device; f->p = owner->p; f->W = owner->W; f->H = owner->H; f->kind = 2;
+    *out = f;
+    return FLUX_OK;
+}
+
+int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, flux_frame *frame, void *cuda_stream) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    if (!frame) return fail(ctx, FLUX_ERR_INVALID, "render: null frame");
+    if (ctx->have_scene && (frame->W != ctx->cam.W || frame->H != ctx->cam.H))
+        return fail(ctx, FLUX_ERR_INVALID, "render: the frame has another size than the scene's image");
+    if (frame->device != ctx->device) return fail(ctx, FLUX_ERR_INVALID, "render: the frame was opened for another device");
+    DeviceGuard g(ctx->device);
+    return render_common(ctx, rows, n_rows, frame->p, (cudaStream_t)cuda_stream, true, true);
+}
+
+int flux_ctx_sync(flux_ctx *ctx) {
+    if (!ctx) return FLUX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FLUX_OK;
+}
+
+int flux_frame_read(flux_frame *f, double *host_rgb) {
+    if (!f || !host_rgb) return FLUX_ERR_INVALID;
+    DeviceGuard g(f->device);
+    if (cudaMemcpy(host_rgb, f->p, (size_t)f->W * f->H * 3 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        g_create_error = std::string("flux_frame_read: ") + cudaGetErrorString(cudaGetLastError());
+        return FLUX_ERR_CUDA;
+    }
+    return FLUX_OK;
+}
+
+int flux_frame_device_ptr(flux_frame *f, void **p) {
+    if (!f || !p) return FLUX_ERR_INVALID;
+    *p = f->p;
+    return FLUX_OK;
+}
+
+int flux_frame_close(flux_frame *f) {
+    if (!f) return FLUX_ERR_INVALID;
+    DeviceGuard g(f->device);
+    if (f->kind == 0) cudaFree(f->p);
+    else if (f->kind == 1) cudaIpcCloseMemHandle(f->p);
+    cudaGetLastError();
+    delete f;
     return FLUX_OK;
 }
 
@@ -1002,7 +1130,7 @@ int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
 
 int flux_set_kernel_mode(flux_ctx *ctx, int mode) {
     if (!ctx) return FLUX_ERR_INVALID;
-    if (mode < 0 || mode > 4) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0..4");
+    if (mode < 0 || mode > 4 || mode == 3) return fail(ctx, FLUX_ERR_INVALID, "flux_set_kernel_mode: mode must be 0, 1, 2 or 4 (3, the first-generation wavefront kernel, was removed)");
     ctx->kernel_mode = mode;
     return FLUX_OK;
 }

@@ -15,14 +15,10 @@ void launch_resolve_accum(const double *accum, double *out, uint32_t npix, doubl
 bool regen_kernel_applicable(const RenderParams &p);
 void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
 
-// Same result, block-local wavefront for spp >= 4096: CTA per pixel, path slots in shared memory, compacted
-// (slot, sphere) candidate pairs, material-sorted shading (render_wave.cu).
-bool wave_kernel_applicable(const RenderParams &p);
-void launch_render_wave(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
-
-// Second-generation block-local wavefront (render_wave2.cu): conservative FP32 slab pre-test from the constant
-// bank, terminated paths regenerated in the sorted item stage, 3 barriers per iteration.  Bit-identical to
-// render_wave.cu's output.
+// Block-local wavefront (render_wave2.cu): CTA per pixel, path slots in shared memory, conservative FP32 slab
+// pre-test from the constant bank, terminated paths regenerated in the material-sorted item stage, 3 barriers per
+// iteration.  (Its first generation, render_wave.cu — compacted (slot, sphere) candidate pairs, 8 barriers — was an
+// A/B relic by the end of round 1 and left the library in round 2; kernel mode 3 is refused.)
 bool wave2_kernel_applicable(const RenderParams &p);
 void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaStream_t stream);
 

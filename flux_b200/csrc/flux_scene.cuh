@@ -81,7 +81,8 @@ struct RenderParams {
     const uint32_t *set_index;  // [H][W]
     const uint32_t *rows;       // [n_rows] image rows to render, ascending
     uint32_t n_rows;
-    double *out;                // [n_rows][W][3]
+    double *out;                // [n_rows][W][3], or with out_by_row the whole frame [H][W][3] (flux_frame)
+    uint32_t out_by_row;        // 1: the pixel of image row r, column c is stored at out[(r * W + c) * 3]
     unsigned long long *counters;  // flux_counters as u64[...] or null
     unsigned int *work_counter;    // dynamic work distribution
     // spheres rounded to f32, {centre x, y, z, radius}, read as constant-bank operands by the conservative slab

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
                 gg *= inv;
                 b *= inv;
             }
-            double *o = p.out + (size_t)pixel * 3;
+            double *o = p.out + (p.out_by_row ? (size_t)row * W + col : (size_t)pixel) * 3;
             o[0] = r;
             o[1] = gg;
             o[2] = b;

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                 gg *= inv;
                 b *= inv;
             }
-            double *out = p.out + (size_t)pixel * 3;
+            double *out = p.out + (p.out_by_row ? (size_t)row * W + col : (size_t)pixel) * 3;
             out[0] = r;
             out[1] = gg;
             out[2] = b;

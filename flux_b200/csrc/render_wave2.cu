@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 g *= inv;
                 b *= inv;
             }
-            double *out = p.out + (size_t)pixel * 3;
+            double *out = p.out + (p.out_by_row ? (size_t)row * W + col : (size_t)pixel) * 3;
             out[0] = r;
             out[1] = g;
             out[2] = b;

@@ -1,9 +1,16 @@
-"""Multi-GPU sharding of the image and the single framebuffer gather.
+"""Multi-GPU sharding of the image and the assembly of the one frame.
 
 Replaces the reference's dynamic row-band queue (manager.rs:100, job.rs:66-88) and flux-node's TCP tile
-distribution: rank r of N owns rows with (row // tile_rows) % N == r; after rendering, ONE
-all_gather of the packed per-rank slices (padded to equal size) and an index_copy un-interleave.
-Works on any torch device/backend (NCCL on GPUs; gloo on CPU for the tests).
+distribution: rank r of N owns rows with (row // tile_rows) % N == r.
+
+Assembly, product path (``PeerFrame``): rank 0 owns ONE framebuffer on its GPU (``flux_frame_create``), hands its
+64-byte CUDA IPC handle to the other ranks, and every rank's render kernel stores its pixels straight into that
+buffer over NVLink / NVSwitch peer memory (``flux_render_row_list_into_frame``) — no gather collective, no packed
+slices, no un-interleave.  What is left of "communication" is one 4-byte all-reduce used as a stream-ordered barrier.
+
+``FrameGather`` is the collective form of the same assembly (ONE all_gather of packed, padded slices and an
+index_copy un-interleave).  It works on any torch device/backend, so the world-size-2 gloo tests exercise the plan
+with it on CPU, and ``bench.py --gather nccl`` keeps it for A/B against the peer-memory path.
 """
 from __future__ import annotations
 
@@ -49,3 +56,53 @@ class FrameGather:
         else:
             self.frame.index_copy_(0, self.row_index[0], self.mine[:len(p.rows[0])])
         return self.frame
+
+
+def exchange_handle(dist, rank: int, handle: Optional[bytes], src: int = 0) -> bytes:
+    """Rank `src` passes its frame handle (64 opaque bytes) to every rank; works on NCCL and gloo groups alike."""
+    if dist is None:
+        if handle is None:
+            raise ValueError("no process group and no handle")
+        return handle
+    box = [handle if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    h = box[0]
+    if not isinstance(h, (bytes, bytearray)) or len(h) != 64:
+        raise RuntimeError("frame handle exchange failed")
+    return bytes(h)
+
+
+class PeerFrame:
+    """The frame every rank renders into (module docstring).  ``render()`` queues this rank's rows; ``barrier()``
+    orders rank 0's later reads after every rank's render, on the device (stream-ordered, no host wait)."""
+
+    def __init__(self, ctx, plan: FramePlan, rank: int, device=None, dist=None, owner_rank: int = 0):
+        self.ctx, self.plan, self.rank, self.dist, self.owner_rank = ctx, plan, rank, dist, owner_rank
+        self.is_owner = rank == owner_rank
+        handle = None
+        if self.is_owner:
+            self.frame = ctx.frame_create(plan.width, plan.height)
+            if plan.world > 1:
+                handle = self.frame.export()
+        if plan.world > 1:
+            handle = exchange_handle(dist, rank, handle, owner_rank)
+            if not self.is_owner:
+                self.frame = ctx.frame_open_ipc(handle, plan.width, plan.height)
+        self._flag = None
+        if plan.world > 1:
+            import torch
+            self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.my_rows = plan.my_rows(rank)
+
+    def render(self, stream_ptr: int = 0):
+        self.ctx.render_row_list_into_frame(self.my_rows, self.frame, stream_ptr)
+
+    def barrier(self):
+        if self.plan.world > 1:
+            self.dist.all_reduce(self._flag)
+
+    def read(self, out=None):
+        return self.frame.read(out)
+
+    def close(self):
+        self.frame.close()

@@ -118,6 +118,32 @@ class GpuContext:
         self._ck(self._lib.flux_render_row_list_device(self._ctx, _capi.as_u32p(rows), rows.shape[0],
                                                        C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
 
+    # ---- multi-GPU frame assembly over NVLink peer memory (include/fluxb200.h, flux_frame_*) ----
+    def frame_create(self, width: int, height: int) -> "Frame":
+        h = C.c_void_p()
+        self._ck(self._lib.flux_frame_create(self._ctx, width, height, C.byref(h)))
+        return Frame(self._lib, h, width, height, owner=True)
+
+    def frame_open_ipc(self, handle: bytes, width: int, height: int) -> "Frame":
+        if len(handle) != _capi.FLUX_FRAME_HANDLE_BYTES:
+            raise ValueError("frame handle must be 64 bytes")
+        h = C.c_void_p()
+        self._ck(self._lib.flux_frame_open_ipc(self._ctx, handle, width, height, C.byref(h)))
+        return Frame(self._lib, h, width, height, owner=False)
+
+    def frame_open_peer(self, owner: "Frame") -> "Frame":
+        h = C.c_void_p()
+        self._ck(self._lib.flux_frame_open_peer(self._ctx, owner._h, C.byref(h)))
+        return Frame(self._lib, h, owner.width, owner.height, owner=False)
+
+    def render_row_list_into_frame(self, rows, frame: "Frame", stream_ptr: int = 0):
+        rows = np.ascontiguousarray(rows, np.uint32)
+        self._ck(self._lib.flux_render_row_list_into_frame(self._ctx, _capi.as_u32p(rows), rows.shape[0], frame._h,
+                                                           C.c_void_p(stream_ptr)))
+
+    def sync(self):
+        self._ck(self._lib.flux_ctx_sync(self._ctx))
+
     def progressive_begin(self, rows):
         rows = np.ascontiguousarray(rows, np.uint32)
         self._prog_shape = rows.shape[0]
@@ -177,6 +203,41 @@ class GpuContext:
         v = C.c_double()
         self._ck(self._lib.flux_measure_fp64_peak(self._ctx, C.byref(v)))
         return v.value
+
+
+class Frame:
+    """One framebuffer [H][W][3] f64 on its owner's GPU that every GPU of the box renders its rows into through
+    peer memory (flux_frame_*; replaces the RowsReady stream into the manager's ImageBuilder, manager.rs:100,156-162)."""
+
+    def __init__(self, lib, handle, width: int, height: int, owner: bool):
+        self._lib, self._h, self.width, self.height, self.owner = lib, handle, width, height, owner
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(_capi.FLUX_FRAME_HANDLE_BYTES)
+        rc = self._lib.flux_frame_export(self._h, buf)
+        if rc != 0:
+            raise FluxError(rc, (self._lib.flux_last_error(None) or b"").decode())
+        return buf.raw
+
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        rc = self._lib.flux_frame_device_ptr(self._h, C.byref(p))
+        if rc != 0:
+            raise FluxError(rc, "flux_frame_device_ptr")
+        return int(p.value)
+
+    def read(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.float64)
+        rc = self._lib.flux_frame_read(self._h, _capi.as_dp(out))
+        if rc != 0:
+            raise FluxError(rc, (self._lib.flux_last_error(None) or b"").decode())
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.flux_frame_close(self._h)
+            self._h = None
 
 
 def shard_rows(image_height: int, tile_rows: int, rank: int, world: int) -> np.ndarray:

@@ -231,6 +231,38 @@ int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
 int flux_render_row_list_device(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows,
                                 double *d_out_rgb, void *cuda_stream);
 
+/* ---- multi-GPU frame assembly over NVLink peer memory ------------------------
+ * Replaces the reference's RowsReady stream from every worker into the manager's one ImageBuilder
+ * (workers.rs:46-64 -> manager.rs:100,156-162; network form workers.rs:119-243): ONE framebuffer
+ * [image_height][image_width][3] f64 lives on the owner's GPU and every GPU of the box renders its rows straight
+ * into it — the render kernel's final per-pixel store goes through an NVLink / NVSwitch peer mapping — so there is
+ * no gather collective, no packed per-GPU slice and no un-interleave copy.  The only cross-GPU synchronisation a
+ * caller needs is "every GPU's render has finished" (flux_ctx_sync + a barrier of its own, or stream order).
+ *
+ *   owner process / thread:  flux_frame_create -> (flux_frame_export) -> ... -> flux_frame_read -> flux_frame_close
+ *   other GPU, same process: flux_frame_open_peer(ctx, owner_frame)        (cudaDeviceEnablePeerAccess)
+ *   other process:           flux_frame_open_ipc(ctx, handle, W, H)        (CUDA IPC memory handle, 64 bytes)
+ *   every GPU:               flux_render_row_list_into_frame(ctx, rows, n_rows, frame, stream)
+ */
+typedef struct flux_frame flux_frame;
+#define FLUX_FRAME_HANDLE_BYTES 64
+int flux_frame_create(flux_ctx *ctx, uint32_t image_width, uint32_t image_height, flux_frame **out);
+/* handle: FLUX_FRAME_HANDLE_BYTES opaque bytes another process on the same box passes to flux_frame_open_ipc. */
+int flux_frame_export(flux_frame *frame, unsigned char *handle);
+int flux_frame_open_ipc(flux_ctx *ctx, const unsigned char *handle, uint32_t image_width, uint32_t image_height,
+                        flux_frame **out);
+int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner_frame, flux_frame **out);
+/* Camera::render for an ascending row list with every row written at its place in `frame` (row r of the image at
+ * frame[r]).  Asynchronous like flux_render_row_list_device: ordered after work already queued on `cuda_stream`
+ * (may be NULL) and that stream is made to wait for the render; flux_ctx_sync waits on the host. */
+int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, flux_frame *frame,
+                                    void *cuda_stream);
+int flux_ctx_sync(flux_ctx *ctx);
+/* Whole frame to host memory (synchronous; any process / GPU that holds the frame may call it). */
+int flux_frame_read(flux_frame *frame, double *host_rgb /* [image_height][image_width][3] */);
+int flux_frame_device_ptr(flux_frame *frame, void **device_ptr);
+int flux_frame_close(flux_frame *frame);
+
 /* Scene::hit (scene.rs:156-160) on an explicit ray batch.
  * origin_xyz, dir_xyz: [n][3]; hit_shape_id[n] = shape id or -1; t[n] = hit
  * distance (undefined on miss: written as +inf). */
@@ -267,9 +299,9 @@ int flux_bvh_hash(const flux_scene_flat *scene, uint64_t *hash);
 
 /* Force the render kernel variant: 0 = auto, 1 = direct (lane group per pixel), 2 = regeneration
  * (warp per pixel with in-warp path regeneration; needs spp >= 64 and a sphere/plane scene),
- * 3 = block-local wavefront (CTA per pixel, compacted candidate pairs, material-sorted shading;
- * needs spp >= 4096, depth <= 8), 4 = second-generation wavefront (same slot/sample schedule and output bits
- * as 3; conservative FP32 box pre-test, sorted regeneration; needs spp >= 256; the auto choice when it applies).  All compute the
+ * 4 = block-local wavefront (CTA per pixel, path slots in shared memory, conservative FP32 box pre-test,
+ * material-sorted shading and regeneration; needs spp >= 256, depth <= 8; the auto choice when it applies);
+ * 3 was its first generation, removed in round 2 and refused with FLUX_ERR_INVALID.  All compute the
  * same per-sample radiance; they differ only in the order of the per-pixel sum (last bits).  Used by parity
  * tests and A/B timing. */
 int flux_set_kernel_mode(flux_ctx *ctx, int mode);

@@ -62,3 +62,34 @@ def test_two_rank_gather_reassembles_frame(height, tile):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert sum(n for _, _, n in res) == height
+
+
+def _handle_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flux_b200.sharding import exchange_handle
+        secret = bytes(range(64))
+        got = exchange_handle(dist, rank, secret if rank == 0 else None, src=0)
+        # the stream-ordered barrier of PeerFrame is a 4-byte all-reduce
+        flag = torch.ones(1, dtype=torch.int32)
+        dist.all_reduce(flag)
+        q.put((rank, got == secret, int(flag[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_frame_handle_exchange():
+    """PeerFrame's host side without a GPU: rank 0's 64-byte frame handle reaches rank 1 unchanged."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_handle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, 2), (1, True, 2)]

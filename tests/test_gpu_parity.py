@@ -315,8 +315,11 @@ def test_regen_kernel_matches_oracle_and_direct(gpu_ctx, demo1, demo2, scene_nam
     assert Hp.rel_err(imgs[1], ref) <= tol
     assert Hp.rel_err(imgs[2], ref) <= tol
     assert cns[1] == cns[2]
+    # a scene without glossy material has no transcendental on the path: every hit / miss / bounce decision is the
+    # oracle's, so the counts are EQUAL; with glossy lobes a grazing decision may flip once in ~1e8 rays
+    has_glossy = any(flat.struct.materials[i].kind == 3 for i in range(flat.struct.n_materials))
     for k, v in cn_o.items():
-        assert abs(cns[2][k] - v) <= max(2, 1e-6 * v), (k, cns[2][k], v)
+        assert abs(cns[2][k] - v) <= (max(2, 1e-6 * v) if has_glossy else 0), (k, cns[2][k], v)
 
 
 def test_regen_kernel_sharding_bitwise(gpu_ctx, demo2):
@@ -367,7 +370,7 @@ def test_wavefront_kernel_matches_oracle_and_regen(gpu_ctx, demo2, scene_name):
     Hp.upload(gpu_ctx, flat, cfg, ss)
     imgs, cns = {}, {}
     try:
-        for mode in (2, 3, 4):
+        for mode in (2, 4):
             gpu_ctx.set_kernel_mode(mode)
             gpu_ctx.enable_counters(True)
             gpu_ctx.reset_counters()
@@ -381,13 +384,14 @@ def test_wavefront_kernel_matches_oracle_and_regen(gpu_ctx, demo2, scene_name):
         gpu_ctx.enable_counters(False)
     ref, cn_o = O.render_rows(flat, cfg, ss, 0, H - 1, counters=True)
     tol = 1e-12 if scene_name == "deterministic" else RADIANCE_RTOL
-    assert Hp.rel_err(imgs[3], ref) <= tol
+    assert Hp.rel_err(imgs[4], ref) <= tol
     assert Hp.rel_err(imgs[2], ref) <= tol
-    assert cns[2] == cns[3] == cns[4]
-    # second-generation wavefront: same slot/sample schedule and summation order as the first -> same bits
-    assert np.array_equal(imgs[4].view(np.uint64), imgs[3].view(np.uint64))
+    assert cns[2] == cns[4]
+    exact = scene_name == "deterministic"   # no glossy material: every decision is the oracle's, so are the counts
     for k, v in cn_o.items():
-        assert abs(cns[3][k] - v) <= max(2, 1e-6 * v), (k, cns[3][k], v)
+        assert abs(cns[4][k] - v) <= (0 if exact else max(2, 1e-6 * v)), (k, cns[4][k], v)
+    with pytest.raises(Exception):
+        gpu_ctx.set_kernel_mode(3)   # the first-generation wavefront kernel left the library in round 2
 
 
 def test_wavefront_kernel_sharding_bitwise(gpu_ctx, demo2):
