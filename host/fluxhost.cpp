@@ -871,6 +871,13 @@ Image GpuWorker::render_job(const SceneData &sd, const JobConfiguration &cfg, do
     std::vector<std::string> errors(world);
     // the reference's timer covers Scene::from_data + Camera::new + all rendering (manager.rs:145-170)
     const auto t0 = std::chrono::steady_clock::now();
+    // ONE frame on the first GPU; every GPU's render kernel stores its rows into it through NVLink peer memory
+    // (flux_frame_*: replaces the RowsReady stream into the manager's ImageBuilder, manager.rs:100,156-162) — no
+    // per-GPU slices in host memory, no assembly on the host; one device-to-host copy at the end.
+    GpuContext &owner = *contexts_[0];
+    flux_frame *frame = nullptr;
+    owner.check(flux_frame_create(owner.get(), W, H, &frame), "flux_frame_create");
+    std::vector<flux_frame *> views(world, nullptr);
     auto shard = [&](uint32_t rank) {
         try {
             uint32_t n = 0;
@@ -879,11 +886,10 @@ Image GpuWorker::render_job(const SceneData &sd, const JobConfiguration &cfg, do
             flux_shard_rows(H, tile_rows_, rank, world, rows.data(), &n);
             if (n == 0) return;
             GpuContext &ctx = *contexts_[rank];
-            Camera camera = Camera::create(ctx, scene, cfg, W, seed_);   // same seed on every GPU: identical sample sets
-            const std::vector<double> px = camera.render_row_list(rows);
-            const size_t row_elems = (size_t)W * 3;
-            for (uint32_t k = 0; k < n; k++)   // disjoint rows: no synchronisation needed
-                std::copy(px.begin() + k * row_elems, px.begin() + (k + 1) * row_elems, img.pixels.begin() + (size_t)rows[k] * row_elems);
+            Camera::create(ctx, scene, cfg, W, seed_);   // same seed on every GPU: identical sample sets
+            ctx.check(flux_frame_open_peer(ctx.get(), frame, &views[rank]), "flux_frame_open_peer");
+            ctx.check(flux_render_row_list_into_frame(ctx.get(), rows.data(), n, views[rank], nullptr), "flux_render_row_list_into_frame");
+            ctx.check(flux_ctx_sync(ctx.get()), "flux_ctx_sync");
         } catch (const std::exception &e) {
             errors[rank] = e.what();
         }
@@ -893,10 +899,18 @@ Image GpuWorker::render_job(const SceneData &sd, const JobConfiguration &cfg, do
     } else {
         std::vector<std::thread> th;
         for (uint32_t r = 0; r < world; r++) th.emplace_back(shard, r);
-        for (auto &t : th) t.join();
+        for (auto &t : th) t.join();   // the join is the barrier: every GPU's rows are in the frame
     }
+    std::string first_error;
     for (const std::string &e : errors)
-        if (!e.empty()) throw Error(e);
+        if (!e.empty() && first_error.empty()) first_error = e;
+    int rc = FLUX_OK;
+    if (first_error.empty()) rc = flux_frame_read(frame, img.pixels.data());
+    for (flux_frame *v : views)
+        if (v) flux_frame_close(v);
+    flux_frame_close(frame);
+    if (!first_error.empty()) throw Error(first_error);
+    if (rc != FLUX_OK) throw Error(std::string("flux_frame_read: ") + flux_last_error(nullptr));
     if (render_seconds) *render_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return img;
 }

@@ -165,7 +165,7 @@ class Camera {
 // are assembled in host memory.
 class GpuWorker {
   public:
-    GpuWorker(std::vector<int> devices, uint64_t seed, uint32_t tile_rows = 4);
+    GpuWorker(std::vector<int> devices, uint64_t seed, uint32_t tile_rows = 1);
     WorkerInfo info() const;
     // workers.rs:46-64 for one job: Scene::from_data, Camera::new, render every work unit -> image
     Image render_job(const SceneData &sd, const JobConfiguration &cfg, double *render_seconds = nullptr);

@@ -53,15 +53,19 @@ def render_config(ctx, name, sd, root, depth=5, seed=1, reps=2):
     return out
 
 
-def c5(ctx, n_total=100_000_000, chunk=10_000_000):
+def c5(ctx, n_total=100_000_000, chunk=10_000_000, reps=1):
     sd = synth.sphere_cloud_scene(10_000, seed=5)
     flat = sd.flatten()
     ctx.set_scene(flat, JobConfiguration(1))
     ms_total, hits, csum = 0.0, 0, 0
     for k in range(n_total // chunk):
         o, d = synth.random_rays(chunk, seed=5, chunk_offset=k)
-        hit, t = ctx.trace_rays(o, d)
-        ms_total += ctx.last_kernel_ms()
+        best = None
+        for _ in range(reps):   # the GPU idles while the host makes the next chunk: repeat and keep the fastest launch
+            hit, t = ctx.trace_rays(o, d)
+            ms = ctx.last_kernel_ms()
+            best = ms if best is None else min(best, ms)
+        ms_total += best
         hits += int((hit >= 0).sum())
         csum = (csum + int(hit.astype(np.int64).sum())) & 0xFFFFFFFFFFFF
     # event counts on the first chunk (the instrumented instantiation is slower: not part of the timing)
@@ -104,6 +108,8 @@ def main():
         render_config(ctx, "c1 demo1 512x512 @16spp", sd, 4, reps=5)
     if "c5" in which:
         c5(ctx)
+    if "c5q" in which:   # quick A/B form: 20 M rays, best of 4 launches per chunk
+        c5(ctx, 20_000_000, 10_000_000, reps=4)
     if "c3" in which:
         render_config(ctx, "c3 1M-triangle mesh 800x600 @1024spp (BVH)", synth.mesh_scene(1000, 500, seed=3), 32)
     if "c4" in which:
