@@ -424,7 +424,6 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         sc.bvh_linear = ctx->bvh_linear.p;
         sc.bvh_n_linear = (uint32_t)bb.linear.size();
         sc.bvh_extent = bb.extent;
-        sc.bvh_ext32 = bb.ext32;
         ctx->bvh_depth = bb.depth;
         ctx->bvh_leaf = bb.leaf_size;
     }

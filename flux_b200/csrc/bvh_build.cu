@@ -216,7 +216,6 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         return false;
     }
     // ---- leaf records ----
-    double sph_cmax = 0.0;
     out.sph.resize(ns);
     for (uint32_t i = 0; i < ns; i++) {
         SphRec &s = out.sph[i];
@@ -226,22 +225,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         s.cx = sph[(size_t)SPH_CX * ns + i]; s.cy = sph[(size_t)SPH_CY * ns + i]; s.cz = sph[(size_t)SPH_CZ * ns + i];
         s.rr = sph[(size_t)SPH_RR * ns + i]; s.r = sph[(size_t)SPH_R * ns + i]; s.inv = sph[(size_t)SPH_INV * ns + i];
         s.shape_id = sph_meta[i]; s.material = sph_meta[ns + i]; s.index = i; s.pad = 0;
-        // f32 copy for the conservative box classification in the leaves (flux_bvh.cuh classify_sphere_box); spheres
-        // that FP32 must never decide — non-finite, huge, negative radius — carry NaN and always take the exact test
-        const bool ok = std::isfinite(s.cx) && std::isfinite(s.cy) && std::isfinite(s.cz) && std::isfinite(s.r) && s.r >= 0.0 &&
-                        std::fabs(s.cx) < 1e30 && std::fabs(s.cy) < 1e30 && std::fabs(s.cz) < 1e30 && s.r < 1e30;
-        const float nanf_ = std::numeric_limits<float>::quiet_NaN();
-        s.f32c[0] = ok ? (float)s.cx : nanf_; s.f32c[1] = ok ? (float)s.cy : nanf_;
-        s.f32c[2] = ok ? (float)s.cz : nanf_; s.f32c[3] = ok ? (float)s.r : nanf_;
-        if (ok) sph_cmax = std::max({sph_cmax, std::fabs(s.cx) + s.r, std::fabs(s.cy) + s.r, std::fabs(s.cz) + s.r});
     }
-    auto set_ext32 = [&] {   // >= the tree's extent and >= |centre_k| + r of every classifiable sphere, rounded up
-        const double e = std::max(out.extent, sph_cmax) * (1.0 + 1e-6);
-        float f = (float)e;
-        if ((double)f < e) f = std::nextafter(f, std::numeric_limits<float>::infinity());
-        out.ext32 = f;
-    };
-    set_ext32();
     out.tri.resize(nt);
     // independent per triangle: in slices on several host threads when there are many
     auto in_slices = [](uint32_t count, const std::function<void(uint32_t, uint32_t)> &body) {
@@ -376,7 +360,6 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     double ext = 0.0;
     for (int k = 0; k < 3; k++) ext = std::max({ext, std::fabs(all.lo[k]), std::fabs(all.hi[k])});
     out.extent = ext;
-    set_ext32();
     B.pad = BVH_PAD_REL * std::max(ext, 1e-300);
 
     lap("oversized");

@@ -42,8 +42,16 @@
 #define BVH_STACK 32          // entries per thread (shared memory); the builder keeps 3*depth+1 below it
 #define BVH_PAD_REL 1e-7
 #define BVH_PRUNE_REL 1e-9
+// Inner nodes a lane may walk per descend() run before the warp moves on to its leaf tests (flux_bvh.cuh descend()).
+// Unbounded is the classic while-while order; a small bound keeps the lanes that need 0-2 nodes to their next leaf
+// from idling behind the few that have just started a ray at the root (~6 nodes).  Measured r2 (one B200):
+// config 5, 20 M rays: unbounded 1841, 1 / 2 / 3 / 4 / 5 nodes 1690 / 2030 / 2175 / 2314 / 2245 Mrays/s;
+// config 3 (regeneration kernel): unbounded 633, 1 / 2 / 3 / 4 / 5 nodes 639 / 675 / 670 / 659 / 653 Msamples/s.
 #ifndef BVH_DESCEND_MAX
-#define BVH_DESCEND_MAX 0xFFFFFFFFu   // inner nodes per descend() run (unbounded = while-while)
+#define BVH_DESCEND_MAX 2u          // closest_hit_bvh: the render kernels (a warp's lanes start their segments together)
+#endif
+#ifndef TRACE_DESCEND_MAX
+#define TRACE_DESCEND_MAX 4u        // trace_rays_bvh_kernel: lanes refill one by one
 #endif
 #ifndef BVH_FIRST_LEAF
 #define BVH_FIRST_LEAF 2      // leaf size tried first by the builder (doubled while the tree is too deep for the stack);
@@ -59,14 +67,12 @@ struct __align__(128) BvhNode4 {
 static_assert(sizeof(BvhNode4) == 128, "BvhNode4 layout");
 
 // leaf records
-struct __align__(16) SphRec {   // 128 B: one line
+struct __align__(16) SphRec {   // 112 B
     double c0x, c1x, c0y, c1y, c0z, c1z;   // bounding box, shapes.rs:156-161
     double cx, cy, cz, rr;
     double r, inv;
     uint32_t shape_id, material, index, pad;
-    float f32c[4];   // centre and radius rounded to f32 for the conservative box classification (NaN: always the exact test)
 };
-static_assert(sizeof(SphRec) == 128, "SphRec layout");
 struct __align__(16) TriRec {   // 80 B... padded to 96
     double v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
     uint32_t shape_id, material;
@@ -76,19 +82,13 @@ struct __align__(16) TriRec {   // 80 B... padded to 96
 #ifdef __CUDACC__
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
-// Sphere::hit distance on a leaf record (same expressions as sphere_t in flux_intersect.cuh).  BoundingBox::hit
-// (shapes.rs:98-133) is first decided in FP32 where that is certain: `cls` is +1 (the reference's test passes), -1 (it
-// fails) or 0 (too close to call, or not classified: then the exact f64 test runs, on reciprocals formed on demand).
+// Sphere::hit distance on a leaf record (same expressions as sphere_t in flux_intersect.cuh).
 template <bool COUNT>
-__device__ __forceinline__ bool sphere_t_rec(RayCtx &r, const SphRec *__restrict__ s, int cls, double &t_out,
+__device__ __forceinline__ bool sphere_t_rec(const RayCtx &r, const SphRec *__restrict__ s, double &t_out,
                                              unsigned long long *cn) {
     if (COUNT) cn[CN_BBOX_TESTS]++;
-    if (cls < 0) return false;
-    if (cls == 0) {
-        ray_need_inv(r);
-        const double2 bx = ldg2(&s->c0x), by = ldg2(&s->c0y), bz = ldg2(&s->c0z);
-        if (!bbox_hit(r, bx.x, by.x, bz.x, bx.y, by.y, bz.y)) return false;
-    }
+    const double2 bx = ldg2(&s->c0x), by = ldg2(&s->c0y), bz = ldg2(&s->c0z);
+    if (!bbox_hit(r, bx.x, by.x, bz.x, bx.y, by.y, bz.y)) return false;
     if (COUNT) cn[CN_BBOX_PASS]++;
     const double2 c01 = ldg2(&s->cx), c23 = ldg2(&s->cz);
     V3 temp = r.o - mk3(c01.x, c01.y, c23.x);
@@ -115,9 +115,13 @@ __device__ __forceinline__ bool tri_t_rec(const RayCtx &r, const TriRec *__restr
     V3 p = cross3(r.d, e2);
     double det = dot3(e1, p);
     if (det == 0.0) return false;
-    double inv = 1.0 / det;
     V3 s = r.o - v0;
-    double u = dot3(s, p) * inv;
+    const double sp = dot3(s, p);
+    // (r2, measured and dropped: rejecting from the signs and magnitudes of sp and det before the IEEE division — exact,
+    // the division is ~25 instructions and most leaf triangles fail the u test — made config 3 slower, 681 against 695
+    // Msamples/s: two more branches in a loop that already runs at 9 of 32 lanes cost more than the divisions saved)
+    double inv = 1.0 / det;
+    double u = sp * inv;
     if (!(u >= 0.0 && u <= 1.0)) return false;
     V3 qv = cross3(s, e1);
     double v = dot3(r.d, qv) * inv;
@@ -142,30 +146,7 @@ struct BvhTraversal {
     double t_prune, tscale, t_prune_seen;
     float t_prune32;
     float ia32[3], nlo[3], nhi[3];
-    float e4;   // 4 max_k E_k + slack: a sphere box whose one-sided f32 interval is longer than this passes for certain
     bool pos[3];
-
-    // BoundingBox::hit of a sphere record in FP32, conservatively: with near'_k = fma(m_k -+ r ..) built on nlo (entry
-    // bounds lowered by E_k) and far'_k on nhi (exit bounds raised by E_k),  F' < N'  means the reference's f64 test
-    // fails (the rule that skips nodes), and  F' - N' > 4 max E_k  means it passes: its t0 <= max near' + 2E and its
-    // t1 >= F' - 2E, so t0 < t1 and t1 > T_MIN + 2E.  E_k bounds the f32 evaluation error of a slab value for any
-    // |coordinate| <= the extent the ray constants were made with (begin()), which covers every valid sphere of the
-    // scene.  Anything else — NaN centre or radius (invalid spheres carry NaN), rays whose constants are not sane
-    // (e4 = NaN) — is undecided.  Same derivation as the box classification of render_wave2.cu.
-    __device__ __forceinline__ int classify_sphere_box(const SphRec *__restrict__ s) const {
-        const float4 c = __ldg(reinterpret_cast<const float4 *>(s->f32c));
-        const float ax = fabsf(ia32[0]), ay = fabsf(ia32[1]), az = fabsf(ia32[2]);
-        const float tlx = fmaf(c.x, ia32[0], nlo[0]), thx = fmaf(c.x, ia32[0], nhi[0]);
-        const float tly = fmaf(c.y, ia32[1], nlo[1]), thy = fmaf(c.y, ia32[1], nhi[1]);
-        const float tlz = fmaf(c.z, ia32[2], nlo[2]), thz = fmaf(c.z, ia32[2], nhi[2]);
-        const float mn = fmaxf(fmaxf(fmaf(-c.w, ax, tlx), fmaf(-c.w, ay, tly)), fmaf(-c.w, az, tlz));
-        const float tf = fminf(fminf(fmaf(c.w, ax, thx), fmaf(c.w, ay, thy)), fmaf(c.w, az, thz));
-        // T_MIN = 0.0005 is not an f32 number: 0.000501f stands above it where t1 > T_MIN must be certain, 0.000499f below
-        // it where t1 < T_MIN must be (as in the node test); every comparison is false for NaN
-        if (tf - fmaxf(mn, 0.000501f) > e4) return 1;
-        if ((tf < mn || tf < 0.000499f) && e4 == e4) return -1;
-        return 0;
-    }
     uint32_t sp, cur;   // cur: inner node index | leaf reference | BVH_EMPTY (done; carries the leaf bit)
 
     __device__ __forceinline__ bool done() const { return cur == BVH_EMPTY; }
@@ -188,7 +169,7 @@ struct BvhTraversal {
         }
     }
 
-    // the f32 ray constants, then the unbounded / oversized shapes (they tighten t_prune before the traversal starts)
+    // unbounded / oversized shapes first (they tighten t_prune early), then the f32 ray constants
     __device__ __forceinline__ void begin(const DevScene &sc, const RayCtx &ray, unsigned long long *cn) {
         r = ray;
         best.t = 0.0;
@@ -196,14 +177,24 @@ struct BvhTraversal {
         best.kind = 0;
         best.index = 0;
         const double inf = __longlong_as_double(0x7FF0000000000000ll);
+        // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k|
+        tscale = sc.bvh_extent * fmin(fabs(r.ia), fmin(fabs(r.ib), fabs(r.ic)));
         t_prune = inf;
+        for (uint32_t i = 0; i < sc.n_planes; i++) {
+            double t;
+            if (COUNT) cn[CN_PLANE_TESTS]++;
+            if (plane_t(r, sc.pln, sc.n_planes, i, t)) candidate(t, __ldg(sc.pln_meta + i), KIND_PLANE, i, cn);
+        }
+        for (uint32_t k = 0; k < sc.bvh_n_linear; k++) {
+            const uint32_t i = __ldg(sc.bvh_linear + k);
+            double t;
+            if (sphere_t<COUNT>(r, sc.sph, sc.n_spheres, i, t, cn)) candidate(t, __ldg(sc.sph_meta + i), KIND_SPHERE, i, cn);
+        }
         sp = 0;
         cur = sc.bvh_n_nodes ? 0u : BVH_EMPTY;   // root
         // f32 ray constants: near = fma(c_near, ia, nlo) <= exact entry, far = fma(c_far, ia, nhi) >= exact exit
         const double dd[3] = {r.d.x, r.d.y, r.d.z}, oo[3] = {r.o.x, r.o.y, r.o.z};
-        const float ext = sc.bvh_ext32;   // >= |coordinate| of every box in the tree and of every valid sphere's box
-        float emax = 0.f, amin = CUDART_INF_F;
-        bool all_sane = true;
+        const float ext = __double2float_ru(sc.bvh_extent);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float df = (float)dd[k], of = (float)oo[k];
@@ -218,35 +209,13 @@ struct BvhTraversal {
             ia32[k] = sane ? a : 0.0f;
             nlo[k] = sane ? noa - E : -CUDART_INF_F;   // an axis that cannot be bounded constrains nothing
             nhi[k] = sane ? noa + E : CUDART_INF_F;
-            emax = fmaxf(emax, E);
-            amin = fminf(amin, fabsf(a));
-            all_sane = all_sane && sane && fabsf(a) < 1e30f;
         }
-        // sphere boxes are classified only for rays whose three axes are all bounded (else: the exact test)
-        e4 = (all_sane && emax > 1e-30f && emax < 1e30f) ? 4.0f * emax + 8e-9f : __int_as_float(0x7fc00000);
-        // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k| (rounded up in f32)
-        tscale = sc.bvh_extent * (double)(amin * 1.0001f);
         t_prune32 = CUDART_INF_F;   // >= t_prune, refreshed lazily
         t_prune_seen = inf;
-        for (uint32_t i = 0; i < sc.n_planes; i++) {
-            double t;
-            if (COUNT) cn[CN_PLANE_TESTS]++;
-            if (plane_t(r, sc.pln, sc.n_planes, i, t)) candidate(t, __ldg(sc.pln_meta + i), KIND_PLANE, i, cn);
-        }
-        // spheres kept out of the tree (environment spheres): the same record test as in the leaves
-        const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
-        for (uint32_t k = 0; k < sc.bvh_n_linear; k++) {
-            const uint32_t i = __ldg(sc.bvh_linear + k);
-            const SphRec *s = srec + i;
-            double t;
-            if (sphere_t_rec<COUNT>(r, s, classify_sphere_box(s), t, cn)) candidate(t, __ldg(&s->shape_id), KIND_SPHERE, i, cn);
-        }
     }
 
     // inner nodes until this lane holds a leaf or has nothing left — or, with max_steps, for at most that many nodes:
-    // the lane may then still hold an inner node (no leaf bit) and simply goes on in the caller's next round.  Bounding
-    // the run keeps the lanes of a warp that need few steps to their next leaf from idling behind the few that have
-    // just started a ray at the root (BVH_DESCEND_MAX, measured in DESIGN.md §8).
+    // the lane may then still hold an inner node (no leaf bit) and goes on in the caller's next round
     __device__ __forceinline__ void descend(const DevScene &sc, uint2 *stack, uint32_t stride, unsigned long long *cn,
                                             uint32_t max_steps = 0xFFFFFFFFu) {
         const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
@@ -307,7 +276,7 @@ struct BvhTraversal {
             double t;
             if ((pr >> 30) == KIND_SPHERE) {
                 const SphRec *s = srec + idx;
-                if (sphere_t_rec<COUNT>(r, s, classify_sphere_box(s), t, cn)) candidate(t, __ldg(&s->shape_id), KIND_SPHERE, idx, cn);
+                if (sphere_t_rec<COUNT>(r, s, t, cn)) candidate(t, __ldg(&s->shape_id), KIND_SPHERE, idx, cn);
             } else {
                 const TriRec *q = trec + idx;
                 if (COUNT) cn[CN_TRI_TESTS]++;
@@ -341,7 +310,6 @@ struct BvhBuild {
     std::vector<uint32_t> linear;    // sphere indices kept out of the tree
     std::vector<SphRec> sph;         // [n_spheres], indexed like the SoA arrays
     std::vector<TriRec> tri;         // [n_triangles]
-    float ext32 = 0.f;               // >= extent and >= |centre_k| + radius of every sphere with an f32 copy, rounded up
     double extent = 0.0;             // max |coordinate| over the boxes in the tree
     uint32_t depth = 0;              // levels of 4-wide nodes
     uint32_t leaf_size = 0;

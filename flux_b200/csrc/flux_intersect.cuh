@@ -15,7 +15,6 @@ struct RayCtx {
     bool pa, pb, pc;      // ia >= 0.0 ...          shapes.rs:108,115,122
     double A;             // d.d                    shapes.rs:177
     double A2, A4;        // 2.0*a, 4.0*a           shapes.rs:187,180
-    bool has_inv;         // ia, ib, ic, pa, pb, pc are set (the BVH traversal forms them only where an exact box test needs them)
 };
 
 __device__ __forceinline__ RayCtx make_ray(V3 o, V3 d) {
@@ -31,38 +30,7 @@ __device__ __forceinline__ RayCtx make_ray(V3 o, V3 d) {
     r.A = dot3(d, d);
     r.A2 = 2.0 * r.A;
     r.A4 = 4.0 * r.A;
-    r.has_inv = true;
     return r;
-}
-
-// The same ray without the three reciprocals (3 IEEE divisions, ~80 instructions): for the BVH traversal, whose node
-// tests run in FP32 and whose leaves decide most sphere boxes in FP32 as well (flux_bvh.cuh); ray_need_inv() completes
-// it — with the very values make_ray forms — on the rare path that runs an exact BoundingBox::hit.
-__device__ __forceinline__ RayCtx make_ray_noinv(V3 o, V3 d) {
-    RayCtx r;
-    r.o = o;
-    r.d = d;
-    r.ia = r.ib = r.ic = 0.0;
-    r.pa = r.pb = r.pc = false;
-    r.A = dot3(d, d);
-    r.A2 = 2.0 * r.A;
-    r.A4 = 4.0 * r.A;
-    r.has_inv = false;
-    return r;
-}
-// (out of line and by value: one copy of the three division expansions per kernel, and the ray stays in registers)
-static __device__ __noinline__ V3 ray_inv3(double dx, double dy, double dz) { return V3{1.0 / dx, 1.0 / dy, 1.0 / dz}; }
-__device__ __forceinline__ void ray_need_inv(RayCtx &r) {
-    if (!r.has_inv) {
-        const V3 inv = ray_inv3(r.d.x, r.d.y, r.d.z);
-        r.ia = inv.x;
-        r.ib = inv.y;
-        r.ic = inv.z;
-        r.pa = r.ia >= 0.0;
-        r.pb = r.ib >= 0.0;
-        r.pc = r.ic >= 0.0;
-        r.has_inv = true;
-    }
 }
 
 struct HitRef {

@@ -58,7 +58,6 @@ struct DevScene {
     uint32_t bvh_n_nodes;
     uint32_t use_bvh;
     double bvh_extent;          // max |coordinate| of the boxes in the tree (scale of the pruning margin)
-    float bvh_ext32;            // >= bvh_extent and >= |centre_k| + radius of every valid sphere (f32 error bounds)
 };
 
 struct DevSamples {

@@ -49,7 +49,7 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
             break;
         }
         if (COUNT) cn[CN_SEGMENTS]++;
-        RayCtx r = BVH ? make_ray_noinv(o, d) : make_ray(o, d);
+        RayCtx r = make_ray(o, d);
         HitRef h = BVH ? closest_hit_bvh<COUNT>(sc, r, stack, blockDim.x, cn) : closest_hit_linear<COUNT>(sc, r, cn);
         if (h.shape_id == 0xFFFFFFFFu) {  // scene.rs:168
             if (COUNT) cn[CN_MISS]++;
@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
                                                          int32_t *__restrict__ hit, double *__restrict__ t) {
     extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x] when BVH
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const V3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-        RayCtx r = BVH ? make_ray_noinv(ro, rd) : make_ray(ro, rd);
+        RayCtx r = make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
         HitRef h = BVH ? closest_hit_bvh<false>(sc, r, bvh_stack + threadIdx.x, blockDim.x, nullptr)
                        : closest_hit_linear<false>(sc, r, nullptr);
         if (h.shape_id == 0xFFFFFFFFu) {
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
             const uint64_t i = next + __popc(need & lt_mask);
             if (i < end) {
                 if (COUNT) cn[CN_SEGMENTS]++;
-                T.begin(sc, make_ray_noinv(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), cn);
+                T.begin(sc, make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), cn);
                 has = true;
                 mine = i;
             }
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_consta
         next += __popc(need);
         if (!__any_sync(0xffffffffu, has)) break;
         if (has) {
-            T.descend(sc, stack, blockDim.x, cn, BVH_DESCEND_MAX);
+            T.descend(sc, stack, blockDim.x, cn, TRACE_DESCEND_MAX);
             if (!T.done() && (T.cur & BVH_LEAF)) T.leaf(sc, stack, blockDim.x, cn);
             if (T.done()) {
                 if (T.best.shape_id == 0xFFFFFFFFu) {

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                 RayCtx rc;
                 HitRef href_bvh;
                 if (BVH) {
-                    rc = make_ray_noinv(o, d);
+                    rc = make_ray(o, d);
                     href_bvh = closest_hit_bvh<COUNT>(p.scene, rc, bvh_stack, blockDim.x, cn);
                     hid = href_bvh.shape_id;
                     t = href_bvh.t;

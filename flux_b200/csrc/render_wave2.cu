@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     uint32_t mi = 0;
                     if (BVH) {
                         uint2 lstack[BVH_STACK];   // local memory: shared memory is taken by the path rows
-                        const RayCtx rc = make_ray_noinv(o, d);
+                        const RayCtx rc = make_ray(o, d);
                         const HitRef h = closest_hit_bvh<COUNT>(p.scene, rc, lstack, 1u, cn);
                         found = h.shape_id != 0xFFFFFFFFu;
                         if (found) {
