@@ -258,8 +258,11 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
 // rays; a lane whose ray is finished takes the chunk's next ray at once (ballot rank, no atomics), so the node loop
 // keeps running with (almost) all lanes instead of waiting for the warp's longest traversal — ncu on the
 // ray-per-thread form showed 6.9 of 32 lanes per instruction (profiles/r1s_bvh_kernels_full.txt).
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 1
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n, uint32_t rays_per_warp,
+__global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n, uint32_t rays_per_warp,
                                                              const double *__restrict__ o, const double *__restrict__ d,
                                                              int32_t *__restrict__ hit, double *__restrict__ t,
                                                              unsigned long long *__restrict__ counters) {

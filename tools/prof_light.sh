@@ -2,7 +2,7 @@
 # Light ncu capture of one render kernel launch (instruction counts per SASS line + scheduler/warp-state
 # stats), cheap enough to run after every kernel change.  usage (on the GPU box): tools/prof_light.sh <tag> [root]
 TAG=${1:-x}; ROOT=${2:-16}
-CMD="python bench.py --root $ROOT --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+CMD="python bench.py --root $ROOT --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 --configs none"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 python - <<PY
 import json
