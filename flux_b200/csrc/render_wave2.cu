@@ -44,6 +44,17 @@
 #define WAVE2_MIN_BLOCKS (1024 / WAVE2_S)   // 64 registers per thread: 32 warps per SM
 #endif
 #define WAVE2_MAX_DEPTH 8    // deeper jobs use the other kernels
+#ifndef WAVE2_OWNER_LIST
+#define WAVE2_OWNER_LIST 1   // owner thread j traces the slot of item j of the iteration before: camera rays (the
+                             // regenerated, "terminated" items, first in the item order) then sit in whole warps
+#endif
+#ifndef WAVE2_BARRIER3
+#define WAVE2_BARRIER3 1     // keep the barrier between the item stage and the next owner stage.  With the owner list it is not
+                             // needed for correctness (see the loop end); measured in DESIGN.md §4.3
+#endif
+#ifndef WAVE2_PMASK
+#define WAVE2_PMASK 1        // ... and those warps classify only the boxes a camera ray of the pixel can reach
+#endif
 #ifndef WAVE2_MIN_SPP
 #define WAVE2_MIN_SPP 256    // measured r1 (demo2): 4.63 / 5.18 / 5.99 / 6.44 / 6.96 Gsamples/s at 256 / 529 / 1024 / 2025 /
                              // 16384 spp against 4.5-4.7 for the regeneration kernel; below 256 the per-pixel drain tail wins
@@ -184,6 +195,60 @@ __device__ __forceinline__ void cull_boxes(const RenderParams &p, const CullRay 
     }
 }
 
+// The same classification for the spheres named by the bits of `m` only (uniform across the warp): the per-pixel
+// primary-ray mask, see primary_mask() below.  One sphere per trip.
+__device__ __forceinline__ void cull_boxes_masked(const RenderParams &p, const CullRay &c, uint32_t base, uint32_t m,
+                                                  uint32_t &okm, uint32_t &failm) {
+#pragma unroll 1
+    while (m) {
+        const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        const uint32_t i = base + j;
+        const float r = p.cull[i][3];
+        const float tcx = fmaf(p.cull[i][0], c.iax, c.nox);
+        const float tcy = fmaf(p.cull[i][1], c.iay, c.noy);
+        const float tcz = fmaf(p.cull[i][2], c.iaz, c.noz);
+        const float tn = fmaxf(fmaxf(fmaf(-r, c.aax, tcx), fmaf(-r, c.aay, tcy)), fmaxf(fmaf(-r, c.aaz, tcz), (float)FLUX_T_MIN));
+        const float tf = fminf(fminf(fmaf(r, c.aax, tcx), fmaf(r, c.aay, tcy)), fmaf(r, c.aaz, tcz));
+        const float sgap = tf - tn;
+        if (sgap > c.e2) okm |= 1u << j;
+        if (sgap < -c.e2) failm |= 1u << j;
+    }
+}
+
+// Per-pixel primary-ray mask.  Every camera ray of a pixel starts on the lens disc (radius R around the eye in the
+// U,V plane, trace.rs:74-79) and passes through the pixel's rectangle on the focal plane (trace.rs:44-51, 72-73): in
+// camera coordinates (U, V, -W) its point at axial distance s is  l (1 - s/f) + q (s/f)  with |l| <= R and q in that
+// rectangle (centre qc, half diagonal rF), for s >= 0.  A sphere's box lies within rho = sqrt(3) |r| of its centre
+// (cu, cv, cs).  With  D(s) = |(cu, cv) - qc s/f| - (R |1 - s/f| + rF s/f)  — Lipschitz in s with constant
+// L = (|qc| + R + rF)/f — no ray of the pixel comes within rho of the centre at any s in [cs - rho, cs + rho] if
+// D(max(cs, 0)) - L rho > rho, or if cs + rho < 0 (behind the lens).  Such a box fails BoundingBox::hit
+// (shapes.rs:98-133) for every primary ray of the pixel, by a margin (1e-6 relative, 1e-9 absolute) that dwarfs the
+// f64 rounding of the reference's slab arithmetic; it is left out of the mask.  Anything non-finite compares false and
+// stays in.  Warps whose rays are all primary then classify 2-3 boxes instead of every sphere of the scene.
+__device__ __forceinline__ bool primary_may_hit(const DevCamera &cam, double colf, double rowf, double cx, double cy, double cz,
+                                                double r) {
+    const double f = cam.focal;
+    if (!(f > 1e-9)) return true;
+    const double k = cam.aps * cam.factor;
+    const double q0u = k * colf, q1u = k * (colf + 1.0), q0v = k * rowf, q1v = k * (rowf + 1.0);
+    const double qcu = 0.5 * (q0u + q1u), qcv = 0.5 * (q0v + q1v);
+    const double rF = 0.5 * sqrt((q1u - q0u) * (q1u - q0u) + (q1v - q0v) * (q1v - q0v)) * (1.0 + 1e-9);
+    const double R = fabs(cam.lens_radius) * (1.0 + 1e-9);
+    const V3 rel = mk3(cx - cam.eye.x, cy - cam.eye.y, cz - cam.eye.z);
+    const double cu = dot3(rel, cam.u), cv = dot3(rel, cam.v), cs = -dot3(rel, cam.w);
+    const double rho = 1.7320508075688774 * fabs(r) * (1.0 + 1e-9);
+    if (cs + rho < 0.0) return false;
+    const double s0 = cs > 0.0 ? cs : 0.0;
+    const double a = s0 / f;
+    const double du = cu - qcu * a, dv = cv - qcv * a;
+    const double D = sqrt(du * du + dv * dv) - (R * fabs(1.0 - a) + rF * a);
+    const double L = (sqrt(qcu * qcu + qcv * qcv) + R + rF) / f;
+    const double scale = fabs(cu) + fabs(cv) + fabs(cs) + rho + R + 1.0;
+    const bool excluded = D - L * rho > rho * (1.0 + 1e-6) + 1e-9 * scale;
+    return !excluded;
+}
+
 // (A/B'd and rejected, r1: prefetch.global.L1 of the hemisphere / lobe sample at classification time and of the next
 // window of camera samples — 6 % slower at both 4096 and 16384 spp; the loads' latency is already covered by the
 // other resident CTAs.)
@@ -199,11 +264,16 @@ struct SphereScan {
 // boxes FP32 could not decide, then the quadratics of the passing spheres in shape order (shapes.rs:176-212).
 template <bool COUNT>
 __device__ __forceinline__ void sphere_pass(const RenderParams &p, const double *sph, const CullRay &c, uint32_t base, uint32_t ns,
-                                            V3 o, V3 d, SphereScan &sc, unsigned long long *cn) {
+                                            V3 o, V3 d, SphereScan &sc, unsigned long long *cn, bool use_pm, uint32_t pm) {
     const uint32_t nsb = ns - base < 32u ? ns - base : 32u;   // spheres in this pass
     uint32_t okm = 0u, failm = 0u;
-    cull_boxes(p, c, base, nsb, okm, failm);
-    const uint32_t valid = nsb >= 32u ? ~0u : ((1u << nsb) - 1u);
+    uint32_t valid = nsb >= 32u ? ~0u : ((1u << nsb) - 1u);
+    if (use_pm) {          // uniform: every tracing lane of the warp carries a camera ray of this pixel
+        valid &= pm;
+        cull_boxes_masked(p, c, base, valid, okm, failm);
+    } else {
+        cull_boxes(p, c, base, nsb, okm, failm);
+    }
     uint32_t mask = okm & valid;
     uint32_t unc = ~(okm | failm) & valid;
     while (unc) {
@@ -305,6 +375,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
     const double pixel_denom = 1.0 / (double)((unsigned long long)p.ss.root * p.ss.root);  // trace.rs:59
     const float cull_scale = 1.01f * 9.5367431640625e-07f;   // 1.01 * 2^-20
     __shared__ uint32_t s_pixel;
+    __shared__ uint32_t s_pm[FLUX_CULL_MAX / 32];   // per-pixel primary-ray mask (primary_may_hit)
     __shared__ double s_red[3][WAVE2_S / 32];
     uint32_t rot = 0;
 #ifdef WAVE2_TIMING
@@ -329,6 +400,17 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
         uint32_t next = 0;   // next unassigned sample index (identical in all threads)
         w.meta[tid] = meta_pack(0, 0, 0, ST_FRESH, T_FRESH);
         w.acc_r[tid] = 0.0; w.acc_g[tid] = 0.0; w.acc_b[tid] = 0.0;
+        uint32_t n_prev = WAVE2_S;   // items of the iteration before = owner threads of this one
+        if (WAVE2_OWNER_LIST) w.list[tid] = tid;
+        if (WAVE2_PMASK && !BVH && !COUNT) {
+            bool may = false;
+            if (tid < ns) {
+                const double *s = w.sph + (size_t)tid * V_SPH_STRIDE;
+                may = primary_may_hit(cam, colf, rowf, s[V_CX], s[V_CY], s[V_CZ], s[V_RB]);
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, may);
+            if (lane == 0 && warp < FLUX_CULL_MAX / 32) s_pm[warp] = b;
+        }
         __syncthreads();
 
         for (;;) {
@@ -336,8 +418,18 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
 #ifdef WAVE2_TIMING
             long long t_prev = clock64();
 #endif
-            uint32_t m = w.meta[tid];
+            // thread -> slot: with WAVE2_OWNER_LIST the slot this thread shaded or regenerated as item `tid` of the
+            // iteration before (read again from the list, which is rewritten only after barrier 1: carrying it in a
+            // register across the iteration cost 60 bytes of spill and 10 % — r2k); else slot `tid`
+            const bool own = !WAVE2_OWNER_LIST || tid < n_prev;
+            const uint32_t sl = WAVE2_OWNER_LIST ? (own ? w.list[tid] : 0u) : tid;
+            uint32_t m = own ? w.meta[sl] : meta_pack(0, 0, 0, ST_IDLE, 0);
             uint32_t kind = K_NONE;
+            bool use_pm = false;
+            if (WAVE2_PMASK && !BVH && !COUNT) {
+                const bool tracing = meta_state(m) == ST_ALIVE && meta_depth(m) <= max_depth;
+                use_pm = __all_sync(0xffffffffu, !tracing || meta_depth(m) == 1u);
+            }
             if (meta_state(m) == ST_FRESH) {
                 kind = K_TERM;   // payload T_FRESH: just generate the first ray
             } else if (meta_state(m) == ST_ALIVE) {
@@ -345,11 +437,11 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 if (depth > max_depth) {   // scene.rs:164-165
                     if (COUNT) cn[CN_DEPTH_CUT]++;
                     kind = K_TERM;
-                    w.meta[tid] = meta_pack(depth, top, 0, ST_ALIVE, T_BLACK);
+                    w.meta[sl] = meta_pack(depth, top, 0, ST_ALIVE, T_BLACK);
                 } else {
                     if (COUNT) cn[CN_SEGMENTS]++;
-                    const V3 o = mk3(w.ox[tid], w.oy[tid], w.oz[tid]);
-                    const V3 d = mk3(w.dx[tid], w.dy[tid], w.dz[tid]);
+                    const V3 o = mk3(w.ox[sl], w.oy[sl], w.oz[sl]);
+                    const V3 d = mk3(w.dx[sl], w.dy[sl], w.dz[sl]);
                     bool found;
                     V3 normal = mk3(0.0, 0.0, 0.0), point = mk3(0.0, 0.0, 0.0);
                     uint32_t mi = 0;
@@ -389,7 +481,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                         sc.best_t = 0.0;
                         sc.best_ref = 0xFFFFFFFFu;  // sphere index; plane = 0x80000000 | index; none = 0xFFFFFFFF
     #pragma unroll 1
-                        for (uint32_t base = 0; base < ns; base += 32) sphere_pass<COUNT>(p, w.sph, c, base, ns, o, d, sc, cn);
+                        for (uint32_t base = 0; base < ns; base += 32) sphere_pass<COUNT>(p, w.sph, c, base, ns, o, d, sc, cn, use_pm, use_pm ? s_pm[base >> 5] : 0u);
                         double best_t = sc.best_t;
                         uint32_t best_ref = sc.best_ref;
                         // ---- planes (shapes.rs:137-139) ----
@@ -433,18 +525,18 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                     if (!found) {  // scene.rs:168
                         if (COUNT) cn[CN_MISS]++;
                         kind = K_TERM;
-                        w.meta[tid] = meta_pack(depth, top, 0, ST_ALIVE, T_BACKGROUND);
+                        w.meta[sl] = meta_pack(depth, top, 0, ST_ALIVE, T_BACKGROUND);
                     } else {
                         const uint32_t mk = w.mat[mi].kind;
                         if (mk == FLUX_MAT_EMISSIVE) {  // materials.rs:42-49
                             if (COUNT) cn[CN_EMISSIVE]++;
                             kind = K_TERM;
-                            w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, dot3(normal * -1.0, d) > 0.0 ? T_EMIT : T_BLACK);
+                            w.meta[sl] = meta_pack(depth, top, mi, ST_ALIVE, dot3(normal * -1.0, d) > 0.0 ? T_EMIT : T_BLACK);
                         } else {
                             kind = mk == FLUX_MAT_MATTE ? K_MATTE : (mk == FLUX_MAT_REFLECTIVE ? K_SPEC : K_GLOSSY);
-                            w.nx[tid] = normal.x; w.ny[tid] = normal.y; w.nz[tid] = normal.z;
-                            w.ox[tid] = point.x; w.oy[tid] = point.y; w.oz[tid] = point.z;  // child ray origin
-                            w.meta[tid] = meta_pack(depth, top, mi, ST_ALIVE, 0);
+                            w.nx[sl] = normal.x; w.ny[sl] = normal.y; w.nz[sl] = normal.z;
+                            w.ox[sl] = point.x; w.oy[sl] = point.y; w.oz[sl] = point.z;  // child ray origin
+                            w.meta[sl] = meta_pack(depth, top, mi, ST_ALIVE, 0);
                         }
                     }
                 }
@@ -454,8 +546,11 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
             // per-warp counts travel as two packed words (matte | specular << 16, glossy | terminated << 16); after the
             // barrier every warp sums the 8 warp totals, and those of the warps before it, with four independent
             // REDUX instructions (the item stage was measured to wait on this dependent chain: tools/wave2_timing.py).
-            // Item order: specular | glossy | terminated | matte — the two expensive kinds (matte, glossy) never share a
-            // warp, so the warp that straddles a boundary pays expensive + cheap, not expensive + expensive.
+            // Item order: terminated | specular | glossy | matte.  The terminated items regenerate camera rays, and with
+            // WAVE2_OWNER_LIST item j's slot is traced by owner thread j of the next iteration: the camera rays start at
+            // thread 0, in whole warps, which is what the per-pixel primary mask needs.  (r1 had the terminated items
+            // between glossy and matte so that the two then most expensive kinds never shared a warp; since the lobe is
+            // no longer evaluated the three kinds cost 4.1 - 4.8 K cycles per warp and the order is free.)
             uint32_t n_matte, n_spec, n_gloss, n_term, pos;
             {
                 const uint32_t bm = __ballot_sync(0xffffffffu, kind == K_MATTE);
@@ -474,14 +569,15 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 const uint32_t bx = __reduce_add_sync(0xffffffffu, lane < warp ? v.x : 0u);
                 const uint32_t by = __reduce_add_sync(0xffffffffu, lane < warp ? v.y : 0u);
                 n_matte = tx & 0xFFFFu; n_spec = tx >> 16; n_gloss = ty & 0xFFFFu; n_term = ty >> 16;
-                pos = rank + (kind == K_SPEC ? (bx >> 16)
-                              : kind == K_GLOSSY ? n_spec + (by & 0xFFFFu)
-                              : kind == K_TERM ? n_spec + n_gloss + (by >> 16)
-                                               : n_spec + n_gloss + n_term + (bx & 0xFFFFu));
+                pos = rank + (kind == K_TERM ? (by >> 16)
+                              : kind == K_SPEC ? n_term + (bx >> 16)
+                              : kind == K_GLOSSY ? n_term + n_spec + (by & 0xFFFFu)
+                                                 : n_term + n_spec + n_gloss + (bx & 0xFFFFu));
             }
             const uint32_t n_items = n_matte + n_spec + n_gloss + n_term;
             if (n_items == 0) break;   // every slot idle (uniform)
-            if (kind != K_NONE) w.list[pos] = tid;
+            if (kind != K_NONE) w.list[pos] = sl;
+            if (WAVE2_OWNER_LIST) n_prev = n_items;
             TMARK(2);
             __syncthreads();
             TMARK(3);
@@ -491,8 +587,8 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 const uint32_t sl = w.list[tid];
                 const uint32_t sm = w.meta[sl];
                 const uint32_t depth = meta_depth(sm), top = meta_top(sm), mi = meta_mat(sm);
-                const uint32_t a_gloss = n_spec, a_term = n_spec + n_gloss, a_matte = a_term + n_term;   // block starts
-                if (tid < a_term || tid >= a_matte) {
+                const uint32_t a_spec = n_term, a_gloss = n_term + n_spec, a_matte = a_gloss + n_gloss;   // block starts
+                if (tid >= a_spec) {
                     const V3 normal = mk3(w.nx[sl], w.ny[sl], w.nz[sl]);
                     const V3 dir = mk3(w.dx[sl], w.dy[sl], w.dz[sl]);
                     const uint32_t i = w.si[sl];
@@ -502,7 +598,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                         if (COUNT) cn[CN_MATTE]++;
                         const double *hp = hs + ((size_t)(depth - 1) * n + i) * 3;
                         matte_sample(normal, mk3(hp[0], hp[1], hp[2]), wi, weight);
-                    } else if (tid < a_gloss) {  // materials.rs:57-71, brdf.rs:39-45
+                    } else if (tid < a_gloss) {  // specular: materials.rs:57-71, brdf.rs:39-45
                         if (COUNT) cn[CN_SPECULAR]++;
                         specular_sample(normal, dir, wi, weight);
                     } else {  // materials.rs:57-71, brdf.rs:55-78
@@ -545,7 +641,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                         w.acc_b[sl] += Lb;
                     }
                     // terminated slots take the pixel's next sample indices in slot order
-                    const uint32_t i = next + (tid - a_term);
+                    const uint32_t i = next + tid;   // the terminated items are the first of the list
                     if (i < n) {
                         const double2 s = ps[i];
                         const double2 l = ds[i];
@@ -573,15 +669,20 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
             {
                 const long long t_now = clock64();
                 if (lane == 0) {
-                    const uint32_t a1 = n_spec + n_gloss, a2 = a1 + n_term;
-                    const int kk = tid >= n_items ? 3 : (tid >= a2 ? 0 : (tid < a1 ? 1 : 2));
+                    const uint32_t a1 = n_term, a2 = a1 + n_spec + n_gloss;
+                    const int kk = tid >= n_items ? 3 : (tid >= a2 ? 0 : (tid < a1 ? 2 : 1));
                     t_acc[7 + 2 * kk] += t_now - t_prev;
                     t_acc[8 + 2 * kk] += 1;
                 }
             }
 #endif
             TMARK(4);
-            __syncthreads();
+            // With WAVE2_OWNER_LIST the thread that handled a slot as an item traces it as its owner: between the item
+            // stage and the next owner stage nothing crosses threads (rows [sl], the stack column and the radiance sum
+            // of a slot are touched by its one thread; `list` is rewritten only after barrier 1, which no thread passes
+            // before all have left this item stage), so this barrier could go — and was measured slower without
+            // (WAVE2_BARRIER3 above).
+            if (!WAVE2_OWNER_LIST || WAVE2_BARRIER3) __syncthreads();
             TMARK(5);
 #ifdef WAVE2_TIMING
             if (lane == 0) t_acc[6] += 1;
