@@ -47,6 +47,7 @@ struct flux_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer ray batches (flux_trace_rays)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
 
@@ -62,6 +63,7 @@ struct flux_ctx {
     int kernel_mode = 0;  // 0 auto, 1 direct (render.cu), 2 regeneration (render_regen.cu), 4 wavefront (render_wave2.cu)
     bool count = false;
     float last_ms = 0.f;
+    bool ms_pending = false;   // last_ms is still to be read from ev0 / ev1 (device-pointer calls do not synchronise)
     uint64_t launches = 0;
 
     DevBuf<double> sph, pln, tri, hemi, out, ray_o, ray_d, ray_t, sink, ghemi, ginv, accum;
@@ -100,6 +102,8 @@ struct flux_ctx {
         bvh_linear.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
         if (stream) cudaStreamDestroy(stream);
         cudaGetLastError();
     }
@@ -669,6 +673,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
         launch_render(p, ctx->count, ctx->sm_count, st);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, st));
+    ctx->ms_pending = true;
     CK(cudaGetLastError());
     if (sync_to_user) CK(cudaStreamWaitEvent(user_stream, ctx->ev1, 0));
     return FLUX_OK;
@@ -931,42 +936,74 @@ int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const d
     launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ms_pending = true;
     CK(cudaGetLastError());
     CK(cudaStreamWaitEvent(us, ctx->ev1, 0));
     return FLUX_OK;
 }
 
+// Host-buffer form: the batch goes through the device in pieces of TRACE_PIECE rays on three streams — upload of
+// piece k+1, traversal of piece k and download of piece k-1 overlap (the PCIe link, 48 bytes in and 12 out per ray, is
+// the bound of this entry point: the kernel alone runs at several times its rate).  Pinned caller memory makes the
+// copies truly asynchronous; pageable memory works, staged by the driver.
 int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d, int32_t *hit, double *t) {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_trace_rays: scene not set");
     if (n == 0) return FLUX_OK;
     if (!o || !d || !hit || !t) return fail(ctx, FLUX_ERR_INVALID, "flux_trace_rays: null pointer");
     DeviceGuard g(ctx->device);
-    const uint64_t chunk = 1ull << 24;  // 16 Mi rays per launch bounds device memory at ~1 GB
-    const uint64_t m = std::min(n, chunk);
-    CK(ctx->ray_o.reserve(3 * m));
-    CK(ctx->ray_d.reserve(3 * m));
-    CK(ctx->ray_t.reserve(m));
-    CK(ctx->ray_hit.reserve(m));
-    float total_ms = 0.f;
-    for (uint64_t off = 0; off < n; off += chunk) {
-        const uint64_t c = std::min(chunk, n - off);
-        CK(cudaMemcpyAsync(ctx->ray_o.p, o + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->ray_d.p, d + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        launch_trace_rays(ctx->scene, c, ctx->ray_o.p, ctx->ray_d.p, ctx->ray_hit.p, ctx->ray_t.p, ctx->sm_count, ctx->stream,
-                          ctx->count ? ctx->counters.p : nullptr);
+    constexpr uint64_t TRACE_PIECE = 1ull << 22;   // 4 Mi rays: 200 MB in, 50 MB out per piece
+    constexpr int NB = 3;
+    const uint64_t piece = std::min<uint64_t>(n, TRACE_PIECE);
+    const int nb = n > piece ? NB : 1;
+    CK(ctx->ray_o.reserve(3 * piece * nb));
+    CK(ctx->ray_d.reserve(3 * piece * nb));
+    CK(ctx->ray_t.reserve(piece * nb));
+    CK(ctx->ray_hit.reserve(piece * nb));
+    if (!ctx->s_in) CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    const uint64_t n_pieces = (n + piece - 1) / piece;
+    struct Ev {
+        std::vector<cudaEvent_t> v;
+        ~Ev() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } ev;   // per piece: uploaded, kernel start, kernel end; per buffer: downloaded
+    ev.v.assign(3 * n_pieces + NB, nullptr);
+    for (size_t k = 0; k < ev.v.size(); k++) {
+        const bool timing = k < 3 * n_pieces && (k % 3) != 0;
+        CK(cudaEventCreateWithFlags(&ev.v[k], timing ? cudaEventDefault : cudaEventDisableTiming));
+    }
+    cudaEvent_t *freed = ev.v.data() + 3 * n_pieces;
+    for (uint64_t k = 0; k < n_pieces; k++) {
+        const uint64_t off = k * piece, c = std::min(piece, n - off);
+        const int b = (int)(k % nb);
+        double *bo = ctx->ray_o.p + 3 * piece * b, *bd = ctx->ray_d.p + 3 * piece * b, *bt = ctx->ray_t.p + piece * b;
+        int32_t *bh = ctx->ray_hit.p + piece * b;
+        if (k >= (uint64_t)nb) CK(cudaStreamWaitEvent(ctx->s_in, freed[b], 0));   // the buffer's last results have left
+        CK(cudaMemcpyAsync(bo, o + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(bd, d + 3 * off, 24 * c, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ev.v[3 * k], ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ev.v[3 * k], 0));
+        CK(cudaEventRecord(ev.v[3 * k + 1], ctx->stream));
+        launch_trace_rays(ctx->scene, c, bo, bd, bh, bt, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr);
         ctx->launches += 1;
-        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventRecord(ev.v[3 * k + 2], ctx->stream));
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(hit + off, ctx->ray_hit.p, 4 * c, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(t + off, ctx->ray_t.p, 8 * c, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_out, ev.v[3 * k + 2], 0));
+        CK(cudaMemcpyAsync(hit + off, bh, 4 * c, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(t + off, bt, 8 * c, cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(freed[b], ctx->s_out));
+    }
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_in));
+    float total_ms = 0.f;
+    for (uint64_t k = 0; k < n_pieces; k++) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ev.v[3 * k + 1], ev.v[3 * k + 2]));
         total_ms += ms;
     }
-    ctx->last_ms = total_ms;
+    ctx->last_ms = total_ms;   // the kernels alone
+    ctx->ms_pending = false;
     return FLUX_OK;
 }
 
@@ -998,9 +1035,10 @@ int flux_last_kernel_ms(flux_ctx *ctx, float *ms) {
     if (!ctx || !ms) return FLUX_ERR_INVALID;
     DeviceGuard g(ctx->device);
     // device-pointer calls do not synchronise: resolve the events lazily here
-    if (cudaEventQuery(ctx->ev1) == cudaSuccess) {
+    if (ctx->ms_pending && cudaEventQuery(ctx->ev1) == cudaSuccess) {
         float v = 0.f;
         if (cudaEventElapsedTime(&v, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = v;
+        ctx->ms_pending = false;
     }
     cudaGetLastError();
     *ms = ctx->last_ms;

@@ -180,3 +180,35 @@ def test_random_scenes_with_triangles_boxes_and_rectangles_render_like_the_oracl
     finally:
         gpu_ctx.set_kernel_mode(0)
         gpu_ctx.set_accel_mode(0)
+
+
+@pytest.mark.parametrize("seed", range(500, 540))
+def test_primary_ray_mask_never_changes_a_pixel(gpu_ctx, seed):
+    """render_wave2.cu classifies, for warps of camera rays, only the boxes its per-pixel bundle test lets through
+    (primary_may_hit).  The instrumented instantiation never uses that mask (it counts every box test, and its counts
+    and pixels are held to the oracle above), so the two must agree bit for bit — on cameras chosen to stress the
+    bundle bound: wide lenses, short and long focal distances, strong zoom, the eye inside or next to spheres, spheres
+    straddling the lens plane and behind it, huge and tiny radii."""
+    rng = np.random.default_rng(seed)
+    sd = random_scene(seed, allow_glossy=bool(seed & 1), width=24, height=16)
+    shapes = list(sd.shapes)
+    eye = np.array(sd.camera_settings.eye)
+    for _ in range(int(rng.integers(2, 10))):     # spheres around the eye: some contain it, some touch the lens disc
+        c = eye + rng.standard_normal(3) * 10.0 ** rng.uniform(-1.5, 0.5)
+        shapes.append(SphereData(tuple(map(float, c)), float(10.0 ** rng.uniform(-2.0, 0.5)), _material(rng, bool(seed & 1)),
+                                 bool(rng.random() < 0.2)))
+    cam = CameraData(float(10.0 ** rng.uniform(-2.0, -0.3)), 500.0, float(10.0 ** rng.uniform(-0.5, 1.5)),
+                     float(rng.choice([0.0, 0.01, 0.3, 2.0])))
+    sd = SceneData(sd.scene_name, sd.output_settings, sd.background, shapes, sd.camera_settings, cam)
+    cfg = JobConfiguration(16, 4, 50)
+    gpu_ctx.set_kernel_mode(4)
+    try:
+        gpu_ctx.set_scene(sd.flatten(), cfg)
+        gpu_ctx.generate_samples(seed, 24)
+        plain = gpu_ctx.render_rows(0, 15, 24)
+        gpu_ctx.enable_counters(True)
+        counted = gpu_ctx.render_rows(0, 15, 24)
+    finally:
+        gpu_ctx.enable_counters(False)
+        gpu_ctx.set_kernel_mode(0)
+    assert np.array_equal(plain.view(np.uint64), counted.view(np.uint64))
