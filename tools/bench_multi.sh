@@ -1,13 +1,15 @@
 #!/bin/bash
-# bench.py on N GPUs of one box, as the driver launches it (torchrun, one rank per GPU), plus the A/B of the frame
-# assembly (peer memory vs NCCL all_gather).  usage: tools/bench_multi.sh N tag
-N=${1:-2}; TAG=${2:-multi}
+# bench.py on N GPUs of one box, as the driver launches it (torchrun, one rank per GPU); with "ab" also the A/B of the
+# frame assembly (peer memory vs NCCL all_gather) and of 4-row tiles.  usage: tools/bench_multi.sh N tag [ab]
+N=${1:-2}; TAG=${2:-multi}; AB=${3:-}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${TAG}_g$N.json 2> gpurun_out/bench_${TAG}_g$N.err
-$TR bench.py --gpus $N --steps 3 --warmup 3 --configs none --gather nccl > gpurun_out/bench_${TAG}_g${N}_nccl.json 2>> gpurun_out/bench_${TAG}_g$N.err
-$TR bench.py --gpus $N --steps 3 --warmup 3 --configs none --gather peer --tile-rows 4 > gpurun_out/bench_${TAG}_g${N}_tile4.json 2>> gpurun_out/bench_${TAG}_g$N.err
-tail -c 1500 gpurun_out/bench_${TAG}_g$N.err
+if [ -n "$AB" ]; then
+  $TR bench.py --gpus $N --steps 3 --warmup 3 --configs none --gather nccl > gpurun_out/bench_${TAG}_g${N}_nccl.json 2>> gpurun_out/bench_${TAG}_g$N.err
+  $TR bench.py --gpus $N --steps 3 --warmup 3 --configs none --gather peer --tile-rows 4 > gpurun_out/bench_${TAG}_g${N}_tile4.json 2>> gpurun_out/bench_${TAG}_g$N.err
+fi
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/bench_${TAG}_g$N.err | tail -c 1500
 for f in gpurun_out/bench_${TAG}_g$N*.json; do python - $f <<'PY'
 import json, sys
 try:
