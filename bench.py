@@ -248,12 +248,27 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
     ctx.set_scene(flat, cfg)
     ctx.generate_samples(seed, W)
     plan = FramePlan(H, W, TILE_ROWS, env.world)
-    pf = PeerFrame(ctx, plan, env.rank, env.dev, env.dist)
+    pf, why = PeerFrame.try_create(ctx, plan, env.rank, env.dev, env.dist)
+    fg = None
+    if pf is None:   # peer-memory frame unavailable: the NCCL gather of packed slices (same fallback as the headline)
+        from flux_b200.sharding import FrameGather
+        fg = FrameGather(plan, env.rank, env.dev, env.dist)
     n_samples = W * H * root * root
+    my_rows = plan.my_rows(env.rank)
 
     def step():
-        pf.render(env.stream)
-        pf.barrier()
+        if pf is not None:
+            pf.render(env.stream)
+            pf.barrier()
+        else:
+            ctx.render_row_list_device(my_rows, fg.mine.data_ptr(), env.stream)
+            fg.gather()
+
+    def read(host):
+        if pf is not None:
+            pf.read(host)
+        else:
+            host[:] = fg.frame.cpu().numpy()
 
     step()                                   # warm-up (these kernels are warm from the headline or trivially short)
     env.barrier()
@@ -271,11 +286,10 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
     flat_b = sd.flatten()                    # Scene::from_data's flattening belongs to the region
     ctx.set_scene(flat_b, cfg)
     ctx.generate_samples(seed, W)
-    pf.render(env.stream)
-    pf.barrier()
+    step()
     torch.cuda.synchronize()
     if env.rank == 0:
-        pf.read(host)
+        read(host)
     env.barrier()
     (e2e_s,) = env.max_over_ranks(time.perf_counter() - t0)
     # event counters on every counter_stride-th row of this rank's shard (the instrumented instantiation is slower)
@@ -285,7 +299,8 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
     ctx.render_row_list(rows, W)
     cn = ctx.counters()
     ctx.enable_counters(False)
-    pf.close()
+    if pf is not None:
+        pf.close()
     keys = sorted(cn)
     tot = dict(zip(keys, env.sum_over_ranks(*[cn[k] for k in keys])))
     scale = n_samples / max(1.0, tot["samples"])
@@ -295,7 +310,8 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
                            " + flux_generate_samples + render + frame to host memory",
            "value_resident": n_samples / (ms * 1e-3) / 1e6, "ms_per_step": ms, "kernel_ms": kernel_ms,
            "h2d_bytes_per_step": int(flat.n_shapes) * 112, "d2h_bytes_per_step": H * W * 24,
-           "segments_per_sample": tot["segments"] / max(1.0, tot["samples"])}
+           "segments_per_sample": tot["segments"] / max(1.0, tot["samples"]),
+           "frame_assembly": "peer" if pf is not None else f"nccl (peer-memory frame unavailable: {why})"}
     if not bvh:
         ops = algorithmic_ops(tot) * scale
         ach = ops / (kernel_ms * 1e-3) / 1e12 / env.world
@@ -498,8 +514,14 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     host_frame = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
     host_np = host_frame.numpy()
+    pf, assembly_note = None, None
     if args.gather == "peer":
-        pf = PeerFrame(ctx, plan, rank, dev, dist)
+        # the product path; if peer access / CUDA IPC is not available on this box every rank agrees to fall back to the
+        # NCCL gather, and the line says so (frame_assembly)
+        pf, why = PeerFrame.try_create(ctx, plan, rank, dev, dist)
+        if pf is None:
+            assembly_note = f"nccl (peer-memory frame unavailable: {why})"
+    if pf is not None:
 
         def step_resident():
             pf.render(stream)
@@ -581,7 +603,7 @@ def main():
            "includes": "region (b): flux_set_scene + flux_generate_samples (device) + render + framebuffer to pinned host memory"}
 
     # ---- roofline: algorithmic FP64 ops of one launch / kernel time vs measured FP64 issue rate
-    if args.gather == "peer":
+    if pf is not None:
         pf.close()
     out_dev = torch.empty((len(my_rows), W, 3), dtype=torch.float64, device=dev)
     ctx.enable_counters(True)
@@ -650,7 +672,7 @@ def main():
             "scaling": "strong", "vs_baseline": value / 5.314, "dtype": "f64", "data": "synthetic",
             "config": workload_config(root, world), "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-            "frame_sha256": frame_sha256, "frame_assembly": args.gather,
+            "frame_sha256": frame_sha256, "frame_assembly": assembly_note or args.gather,
             "kernel_ms_max_over_ranks": kernel_ms_max, "kernel_ms_min_over_ranks": kernel_ms_min,
             "assembly_ms_per_step": ms_per_step - kernel_ms_max,
             "render_time_s_16384spp": W * H * 16384 / (value * 1e6),

@@ -94,6 +94,48 @@ class PeerFrame:
             self._flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.my_rows = plan.my_rows(rank)
 
+    @classmethod
+    def try_create(cls, ctx, plan: FramePlan, rank: int, device=None, dist=None, owner_rank: int = 0):
+        """PeerFrame on every rank, or (None, reason) on every rank: a rank that cannot create / export / map the
+        frame (peer access or CUDA IPC unavailable) must not leave the others waiting in a collective, so every step
+        that can fail is followed by an agreement.  Returns (frame, None) or (None, reason)."""
+        self = cls.__new__(cls)
+        self.ctx, self.plan, self.rank, self.dist, self.owner_rank = ctx, plan, rank, dist, owner_rank
+        self.is_owner = rank == owner_rank
+        self.frame, self._flag = None, None
+        self.my_rows = plan.my_rows(rank)
+        msg = None
+        if self.is_owner:
+            try:
+                self.frame = ctx.frame_create(plan.width, plan.height)
+                msg = self.frame.export() if plan.world > 1 else b""
+            except Exception as e:   # noqa: BLE001 — the reason travels to every rank
+                msg = f"rank {rank}: {e}"
+        if plan.world == 1:
+            return (self, None) if self.frame is not None else (None, msg)
+        box = [msg if self.is_owner else None]
+        dist.broadcast_object_list(box, src=owner_rank)
+        msg = box[0]
+        reason = None
+        if not isinstance(msg, (bytes, bytearray)) or len(msg) != 64:
+            reason = str(msg)
+        elif not self.is_owner:
+            try:
+                self.frame = ctx.frame_open_ipc(bytes(msg), plan.width, plan.height)
+            except Exception as e:   # noqa: BLE001
+                reason = f"rank {rank}: {e}"
+        import torch
+        ok = torch.tensor([0 if reason else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            reasons = [None] * plan.world
+            dist.all_gather_object(reasons, reason)
+            if self.frame is not None:
+                self.frame.close()
+            return None, "; ".join(r for r in reasons if r) or "unknown"
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        return self, None
+
     def render(self, stream_ptr: int = 0):
         self.ctx.render_row_list_into_frame(self.my_rows, self.frame, stream_ptr)
 
