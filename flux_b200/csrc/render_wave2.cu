@@ -48,6 +48,9 @@
 #define WAVE2_OWNER_LIST 1   // owner thread j traces the slot of item j of the iteration before: camera rays (the
                              // regenerated, "terminated" items, first in the item order) then sit in whole warps
 #endif
+#ifndef WAVE2_ORDER
+#define WAVE2_ORDER 0         // item order after the terminated items: 0 specular | glossy | matte, 1 matte | specular | glossy
+#endif
 #ifndef WAVE2_BARRIER3
 #define WAVE2_BARRIER3 1     // keep the barrier between the item stage and the next owner stage.  With the owner list it is not
                              // needed for correctness (see the loop end); measured in DESIGN.md §4.3
@@ -569,10 +572,17 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 const uint32_t bx = __reduce_add_sync(0xffffffffu, lane < warp ? v.x : 0u);
                 const uint32_t by = __reduce_add_sync(0xffffffffu, lane < warp ? v.y : 0u);
                 n_matte = tx & 0xFFFFu; n_spec = tx >> 16; n_gloss = ty & 0xFFFFu; n_term = ty >> 16;
+#if WAVE2_ORDER == 0   // terminated | specular | glossy | matte
                 pos = rank + (kind == K_TERM ? (by >> 16)
                               : kind == K_SPEC ? n_term + (bx >> 16)
                               : kind == K_GLOSSY ? n_term + n_spec + (by & 0xFFFFu)
                                                  : n_term + n_spec + n_gloss + (bx & 0xFFFFu));
+#else                  // terminated | matte | specular | glossy
+                pos = rank + (kind == K_TERM ? (by >> 16)
+                              : kind == K_MATTE ? n_term + (bx & 0xFFFFu)
+                              : kind == K_SPEC ? n_term + n_matte + (bx >> 16)
+                                               : n_term + n_matte + n_spec + (by & 0xFFFFu));
+#endif
             }
             const uint32_t n_items = n_matte + n_spec + n_gloss + n_term;
             if (n_items == 0) break;   // every slot idle (uniform)
@@ -587,18 +597,24 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 const uint32_t sl = w.list[tid];
                 const uint32_t sm = w.meta[sl];
                 const uint32_t depth = meta_depth(sm), top = meta_top(sm), mi = meta_mat(sm);
+#if WAVE2_ORDER == 0
                 const uint32_t a_spec = n_term, a_gloss = n_term + n_spec, a_matte = a_gloss + n_gloss;   // block starts
-                if (tid >= a_spec) {
+                const bool is_matte = tid >= a_matte, is_spec = tid < a_gloss;
+#else
+                const uint32_t a_matte = n_term, a_spec = n_term + n_matte, a_gloss = a_spec + n_spec;
+                const bool is_matte = tid < a_spec, is_spec = tid < a_gloss;
+#endif
+                if (tid >= n_term) {
                     const V3 normal = mk3(w.nx[sl], w.ny[sl], w.nz[sl]);
                     const V3 dir = mk3(w.dx[sl], w.dy[sl], w.dz[sl]);
                     const uint32_t i = w.si[sl];
                     V3 wi;
                     double weight, lobe = 1.0;
-                    if (tid >= a_matte) {  // materials.rs:19-33
+                    if (is_matte) {  // materials.rs:19-33
                         if (COUNT) cn[CN_MATTE]++;
                         const double *hp = hs + ((size_t)(depth - 1) * n + i) * 3;
                         matte_sample(normal, mk3(hp[0], hp[1], hp[2]), wi, weight);
-                    } else if (tid < a_gloss) {  // specular: materials.rs:57-71, brdf.rs:39-45
+                    } else if (is_spec) {  // specular: materials.rs:57-71, brdf.rs:39-45
                         if (COUNT) cn[CN_SPECULAR]++;
                         specular_sample(normal, dir, wi, weight);
                     } else {  // materials.rs:57-71, brdf.rs:55-78
