@@ -93,3 +93,56 @@ def test_two_rank_frame_handle_exchange():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, 2), (1, True, 2)]
+
+
+class _NoPeerCtx:
+    """Stands in for a GpuContext on a box without peer access / CUDA IPC."""
+
+    def __init__(self, fail_on):
+        self.fail_on = fail_on
+
+    def frame_create(self, w, h):
+        if self.fail_on == "create":
+            raise RuntimeError("cudaMalloc: no device")
+
+        class _F:
+            def export(self_inner):
+                return bytes(64)
+
+            def close(self_inner):
+                pass
+        return _F()
+
+    def frame_open_ipc(self, handle, w, h):
+        raise RuntimeError("cudaIpcOpenMemHandle: invalid device context")
+
+
+def _fallback_worker(rank, world, port, fail_on, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flux_b200.sharding import FramePlan, PeerFrame
+        plan = FramePlan(12, 8, 1, world)
+        pf, why = PeerFrame.try_create(_NoPeerCtx(fail_on), plan, rank, torch.device("cpu"), dist)
+        q.put((rank, pf is None, why))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_on", ["create", "open"])
+def test_peer_frame_failure_is_agreed_by_every_rank(fail_on):
+    """If the owner cannot create the frame, or another rank cannot map it, no rank is left waiting in a collective:
+    all of them get (None, reason) and bench.py falls back to the NCCL gather together."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fallback_worker, args=(r, world, port, fail_on, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(none for _, none, _ in res)
+    assert res[0][2] == res[1][2] and ("cudaMalloc" in res[0][2] or "cudaIpcOpenMemHandle" in res[0][2])
