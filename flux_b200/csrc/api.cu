@@ -79,6 +79,7 @@ struct flux_ctx {
     DevBuf<double2> pixel, disc;
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned int> work_counter;
+    DevBuf<unsigned long long> trace_work;   // chunk counter of the ray-batch kernel
     // BVH extension (flux_bvh.cuh)
     DevBuf<BvhNode4> bvh_nodes;
     DevBuf<SphRec> bvh_sph;
@@ -98,7 +99,7 @@ struct flux_ctx {
         ray_t.release(); sink.release(); ghemi.release(); ginv.release(); accum.release();
         sph_meta.release(); pln_meta.release(); tri_meta.release(); set_index.release(); rows.release();
         ray_hit.release(); materials.release(); pixel.release(); disc.release(); counters.release();
-        work_counter.release(); bvh_nodes.release(); bvh_sph.release(); bvh_tri.release(); bvh_prims.release();
+        work_counter.release(); trace_work.release(); bvh_nodes.release(); bvh_sph.release(); bvh_tri.release(); bvh_prims.release();
         bvh_linear.release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -234,7 +235,7 @@ int flux_ctx_create(int device, flux_ctx **out) {
         return FLUX_ERR_NO_DEVICE;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    if (ctx->counters.reserve(CN_COUNT) != cudaSuccess || ctx->work_counter.reserve(1) != cudaSuccess ||
+    if (ctx->counters.reserve(CN_COUNT) != cudaSuccess || ctx->work_counter.reserve(1) != cudaSuccess || ctx->trace_work.reserve(1) != cudaSuccess ||
         ctx->sink.reserve(1) != cudaSuccess) {
         g_create_error = "flux_ctx_create: cudaMalloc failed";
         delete ctx;
@@ -933,7 +934,7 @@ int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const d
     CK(cudaEventRecord(ctx->ev1, us));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr);
+    launch_trace_rays(ctx->scene, n, d_o, d_d, d_hit, d_t, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr, ctx->trace_work.p);
     ctx->launches += 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ms_pending = true;
@@ -984,7 +985,7 @@ int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d,
         CK(cudaEventRecord(ev.v[3 * k], ctx->s_in));
         CK(cudaStreamWaitEvent(ctx->stream, ev.v[3 * k], 0));
         CK(cudaEventRecord(ev.v[3 * k + 1], ctx->stream));
-        launch_trace_rays(ctx->scene, c, bo, bd, bh, bt, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr);
+        launch_trace_rays(ctx->scene, c, bo, bd, bh, bt, ctx->sm_count, ctx->stream, ctx->count ? ctx->counters.p : nullptr, ctx->trace_work.p);
         ctx->launches += 1;
         CK(cudaEventRecord(ev.v[3 * k + 2], ctx->stream));
         CK(cudaGetLastError());

@@ -24,8 +24,7 @@ void launch_render_wave2(const RenderParams &p, bool count, int sm_count, cudaSt
 
 // Scene::hit on an explicit ray batch (scene.rs:156-160).
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
-                       int sm_count, cudaStream_t stream,
-                       unsigned long long *counters = nullptr);
+                       int sm_count, cudaStream_t stream, unsigned long long *counters, unsigned long long *work);
 
 // MasterSampleSets::new on the device (sampling.rs:13-33) + per-row set-index permutations (sampling.rs:35-40).
 void launch_generate_samples(uint64_t seed, uint32_t root, uint32_t max_depth, uint32_t num_sets, double2 *pixel,

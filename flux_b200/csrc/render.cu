@@ -254,24 +254,30 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
     }
 }
 
-// BVH variant with per-lane ray refill (persistent "while-while" traversal): a warp owns a contiguous chunk of
-// rays; a lane whose ray is finished takes the chunk's next ray at once (ballot rank, no atomics), so the node loop
-// keeps running with (almost) all lanes instead of waiting for the warp's longest traversal — ncu on the
-// ray-per-thread form showed 6.9 of 32 lanes per instruction (profiles/r1s_bvh_kernels_full.txt).
+// BVH variant with per-lane ray refill (persistent "while-while" traversal in bounded runs): a lane whose ray is
+// finished takes the next ray of its warp's current chunk at once (ballot rank, no atomics), so the node loop keeps
+// running with most lanes instead of waiting for the warp's longest traversal — ncu on the ray-per-thread form showed
+// 6.9 of 32 lanes per instruction (profiles/r1s_bvh_kernels_full.txt), 9.2 with the refill, 16.1 with bounded runs
+// (profiles/r2h_bvh_kernels_full.txt).  Chunks of TRACE_CHUNK rays come from one global counter (one atomic per chunk),
+// so a launch of any size ends with every warp busy until the rays run out: with r1's static split of the batch into
+// equal shares per warp a 4 - 6 M-ray launch spent its last wave half empty.
+#ifndef TRACE_CHUNK
+#define TRACE_CHUNK 128u
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 1
 #endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n, uint32_t rays_per_warp,
+__global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n,
+                                                             unsigned long long *__restrict__ work,
                                                              const double *__restrict__ o, const double *__restrict__ d,
                                                              int32_t *__restrict__ hit, double *__restrict__ t,
                                                              unsigned long long *__restrict__ counters) {
     extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x]
     uint2 *stack = bvh_stack + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint64_t next = warp_global * rays_per_warp;
-    const uint64_t end = next + rays_per_warp < n ? next + rays_per_warp : n;
+    uint64_t next = 0, end = 0;   // the warp's current chunk (uniform)
+    bool exhausted = false;
     BvhTraversal<COUNT> T;
     unsigned long long cn[COUNT ? CN_COUNT : 1];
     if (COUNT)
@@ -280,17 +286,35 @@ __global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(c
     uint64_t mine = 0;
     for (;;) {
         const uint32_t need = __ballot_sync(0xffffffffu, !has);
-        if (!has) {
-            const uint64_t i = next + __popc(need & lt_mask);
-            if (i < end) {
-                if (COUNT) cn[CN_SEGMENTS]++;
-                T.begin(sc, make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), cn);
-                has = true;
-                mine = i;
+        if (need != 0u && !exhausted) {
+            if (next >= end) {   // uniform: fetch the next chunk of the batch
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)TRACE_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) {
+                    exhausted = true;
+                    next = end = n;
+                } else {
+                    next = base;
+                    end = base + TRACE_CHUNK < n ? base + TRACE_CHUNK : n;
+                }
             }
+            if (!has) {
+                const uint64_t i = next + __popc(need & lt_mask);
+                if (i < end) {
+                    if (COUNT) cn[CN_SEGMENTS]++;
+                    T.begin(sc, make_ray(mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2])), cn);
+                    has = true;
+                    mine = i;
+                }
+            }
+            const uint64_t adv = next + __popc(need);
+            next = adv < end ? adv : end;   // lanes left without a ray ask again next round (from the next chunk)
         }
-        next += __popc(need);
-        if (!__any_sync(0xffffffffu, has)) break;
+        if (!__any_sync(0xffffffffu, has)) {
+            if (exhausted) break;
+            continue;
+        }
         if (has) {
             T.descend(sc, stack, blockDim.x, cn, TRACE_DESCEND_MAX);
             if (!T.done() && (T.cur & BVH_LEAF)) T.leaf(sc, stack, blockDim.x, cn);
@@ -313,26 +337,24 @@ __global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(c
     }
 }
 
-// largest chunk of rays per warp (measured r1, config 5 in 10 M-ray launches: 64 / 128 / 256 / 512 / 2048 rays ->
-// 1405 / 1460 / 1756 / 1782 / 1654 Mrays/s: small chunks pay the refill tail, large ones leave a ragged last wave)
-#ifndef TRACE_RPW_MAX
-#define TRACE_RPW_MAX 512
+#ifndef TRACE_CTAS_PER_SM
+#define TRACE_CTAS_PER_SM 5
 #endif
 void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const double *d, int32_t *hit, double *t,
-                       int sm_count, cudaStream_t stream, unsigned long long *counters) {
+                       int sm_count, cudaStream_t stream, unsigned long long *counters, unsigned long long *work) {
     if (n == 0) return;
     const int threads = 128;
     uint64_t want = (n + threads - 1) / threads;
     if (sc.use_bvh) {
-        // chunk of rays per warp: large enough to amortise the refill tail, small enough for >= 16 warps per SM
-        uint64_t rpw = (n + (uint64_t)sm_count * 16 - 1) / ((uint64_t)sm_count * 16);
-        rpw = rpw < 32 ? 32 : (rpw > TRACE_RPW_MAX ? TRACE_RPW_MAX : rpw);
-        const uint64_t warps = (n + rpw - 1) / rpw;
+        // persistent grid: as many CTAs as stay resident (5 per SM at 96 registers and 32 KB of traversal stacks), fed
+        // from the chunk counter `work` (zeroed here, on the launching stream)
         const size_t smem = (size_t)BVH_STACK * threads * sizeof(uint2);
-        const int blocks = (int)((warps * 32 + threads - 1) / threads);
+        const uint64_t cap = (uint64_t)sm_count * TRACE_CTAS_PER_SM;
+        const int blocks = (int)(want < cap ? want : cap);
+        cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream);
         // with counters (flux_enable_counters): segments = rays, nodes_visited, bbox / triangle tests, candidates, misses
-        if (counters) trace_rays_bvh_kernel<true><<<blocks, threads, smem, stream>>>(sc, n, (uint32_t)rpw, o, d, hit, t, counters);
-        else trace_rays_bvh_kernel<false><<<blocks, threads, smem, stream>>>(sc, n, (uint32_t)rpw, o, d, hit, t, nullptr);
+        if (counters) trace_rays_bvh_kernel<true><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, counters);
+        else trace_rays_bvh_kernel<false><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, nullptr);
     } else {
         uint64_t cap = (uint64_t)sm_count * 16;
         int blocks = (int)(want < cap ? want : cap);
