@@ -194,6 +194,24 @@ def test_cli_renders_the_same_ppm_as_the_python_mirror(fluxb200, tmp_path):
     assert out.read_text().startswith("P3\n64 48\n65535\n")
 
 
+@pytest.mark.gpu
+def test_cli_on_two_gpus_writes_the_one_gpu_frame(fluxb200, tmp_path):
+    """fluxb200 -G 2: one host thread per GPU, both kernels storing their rows into one frame on GPU 0 through
+    cudaDeviceEnablePeerAccess (flux_frame_open_peer) — the PPM must be the 1-GPU PPM byte for byte.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    scene = os.path.join(ROOT, "scenes", "demo2.yml")
+    outs = []
+    for g in ("1", "2"):
+        out = tmp_path / f"g{g}.ppm"
+        r = subprocess.run([fluxb200, scene, "-r", "16", "--width", "96", "--height", "70", "-G", g, "-o", str(out)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1]
+
+
 def _scenes_to_write():
     from flux_b200 import (CameraData, CameraSettings, Emissive, Matte, OutputSettings, PlaneData, SphereData, synth)
     from tests import helpers as Hp
