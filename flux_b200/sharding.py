@@ -130,8 +130,7 @@ class PeerFrame:
         if int(ok[0]) == 0:
             reasons = [None] * plan.world
             dist.all_gather_object(reasons, reason)
-            if self.frame is not None:
-                self.frame.close()
+            self.close()   # mappings first, then (after a barrier) the owner's allocation
             return None, "; ".join(r for r in reasons if r) or "unknown"
         self._flag = torch.zeros(1, dtype=torch.int32, device=device)
         return self, None
@@ -147,4 +146,14 @@ class PeerFrame:
         return self.frame.read(out)
 
     def close(self):
-        self.frame.close()
+        """Unmap / free the frame.  The owner frees its allocation only after every other rank has closed its IPC
+        mapping (freeing exported memory that another process still has open is undefined)."""
+        if self.frame is None:
+            return
+        if self.plan.world > 1 and not self.is_owner:
+            self.frame.close()
+        if self.plan.world > 1:
+            self.dist.barrier()
+        if self.plan.world == 1 or self.is_owner:
+            self.frame.close()
+        self.frame = None

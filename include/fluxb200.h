@@ -258,7 +258,10 @@ int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner_frame, flux_frame **ou
 int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, flux_frame *frame,
                                     void *cuda_stream);
 int flux_ctx_sync(flux_ctx *ctx);
-/* Whole frame to host memory (synchronous; any process / GPU that holds the frame may call it). */
+/* Whole frame to host memory (a blocking copy; any process / GPU that holds the frame may call it).  It does not
+ * wait for renders still in flight: the caller orders it after them (flux_ctx_sync on every context that rendered
+ * into the frame, and its own barrier across processes).  The owner must not close the frame while another process
+ * still has it open. */
 int flux_frame_read(flux_frame *frame, double *host_rgb /* [image_height][image_width][3] */);
 int flux_frame_device_ptr(flux_frame *frame, void **device_ptr);
 int flux_frame_close(flux_frame *frame);
