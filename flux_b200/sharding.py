@@ -148,12 +148,15 @@ class PeerFrame:
     def close(self):
         """Unmap / free the frame.  The owner frees its allocation only after every other rank has closed its IPC
         mapping (freeing exported memory that another process still has open is undefined)."""
-        if self.frame is None:
+        if getattr(self, "_closed", False):
             return
-        if self.plan.world > 1 and not self.is_owner:
-            self.frame.close()
-        if self.plan.world > 1:
+        self._closed = True
+        if self.plan.world > 1:   # every rank takes part in the barrier, with or without a mapping of its own
+            if not self.is_owner and self.frame is not None:
+                self.frame.close()
             self.dist.barrier()
-        if self.plan.world == 1 or self.is_owner:
+            if self.is_owner and self.frame is not None:
+                self.frame.close()
+        elif self.frame is not None:
             self.frame.close()
         self.frame = None
