@@ -656,7 +656,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     // automatic choice on BVH scenes (measured r1): the wavefront kernel wins while the tree is small (config 4, 67
     // spheres: 2.72 vs 1.90 Gsamples/s), the regeneration kernel on deep trees whose traversal lengths vary a lot
     // (config 3, 1 M triangles: 567 vs 426 Msamples/s)
-    const bool wave2_auto = wave2_ok && (!p.scene.use_bvh || p.scene.bvh_n_nodes <= 1024);
+    const bool wave2_auto = wave2_ok && (!p.scene.use_bvh || p.scene.bvh_n_nodes <= 2048);   // (1024 while leaves held two primitives: the same scenes)
     // ... and on sphere/plane scenes the wavefront kernel's FP32-culled linear scan beats its own BVH owner stage up
     // to about 120 spheres (measured r1, config-4 scene with 40 / 85 / 125 spheres: 5.21 vs 2.69, 2.98 vs 2.34, 2.29 vs
     // 2.32 Gsamples/s), so a BVH built for the other kernels is left aside here unless it was asked for

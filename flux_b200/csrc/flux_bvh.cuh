@@ -51,11 +51,14 @@
 #define BVH_DESCEND_MAX 2u          // closest_hit_bvh: the render kernels (a warp's lanes start their segments together)
 #endif
 #ifndef TRACE_DESCEND_MAX
-#define TRACE_DESCEND_MAX 4u        // trace_rays_bvh_kernel: lanes refill one by one
+#define TRACE_DESCEND_MAX 8u        // trace_rays_bvh_kernel: lanes refill one by one (4 while leaves held two primitives; with
+                                    // leaves of one, r2F: 4 / 6 / 8 = 2496 / 2562 / 2600 Mrays/s)
 #endif
 #ifndef BVH_FIRST_LEAF
-#define BVH_FIRST_LEAF 2      // leaf size tried first by the builder (doubled while the tree is too deep for the stack);
-                              // measured r1: 2 vs 4 = +8 % on config 5, +1 % on config 3
+#define BVH_FIRST_LEAF 1      // leaf size tried first by the builder (doubled while the tree is too deep for the stack);
+                              // measured r1: 2 vs 4 = +8 % on config 5, +1 % on config 3; r2, with bounded descend runs
+                              // (r2E, one box): 1 / 2 / 4 = 2497 / 2192 / 1970 Mrays/s on config 5, 745 / 695 / 683
+                              // Msamples/s on config 3 — a leaf visit is an f64 primitive test, a node visit four f32 ones
 #endif
 
 struct __align__(128) BvhNode4 {

@@ -130,8 +130,8 @@ def test_bvh_builder_invariants_sphere_cloud():
     d = _describe(flat)
     assert d["violations"] == 0 and d["miscount"] == 0
     assert d["refs"] + d["linear"] == 10_000 and d["linear"] == 0
-    assert d["auto"] == 1 and 3 * d["levels"] + 1 <= 32 and d["leaf"] == 2
-    assert d["nodes"] < 10_000 // 2
+    assert d["auto"] == 1 and 3 * d["levels"] + 1 <= 32 and d["leaf"] == 1   # leaves of one primitive since r2 (+14 % on config 5)
+    assert d["nodes"] < 10_000
 
 
 def test_bvh_builder_keeps_oversized_spheres_linear_and_handles_meshes():
