@@ -1124,9 +1124,10 @@ int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
         const Job j = stack.back();
         stack.pop_back();
         if (j.ref & BVH_LEAF) {
-            const uint32_t off = (j.ref & 0x7FFFFFFFu) >> 3, cnt = (j.ref & 7u) + 1u;
+            const bool direct = (j.ref & BVH_DIRECT) != 0u;
+            const uint32_t off = (j.ref & 0x3FFFFFFFu) >> 3, cnt = direct ? 1u : (j.ref & 7u) + 1u;
             for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t pr = bb.prims[off + k], idx = pr & 0x3FFFFFFFu;
+                const uint32_t pr = direct ? (((j.ref >> 28) & 3u) << 30) | (j.ref & 0x0FFFFFFFu) : bb.prims[off + k], idx = pr & 0x3FFFFFFFu;
                 double lo[3], hi[3];
                 if ((pr >> 30) == KIND_SPHERE) {
                     seen_s[idx]++;

@@ -119,7 +119,11 @@ struct Builder {
     }
     uint32_t make_leaf(uint32_t a, uint32_t b) {
         const uint32_t off = (uint32_t)out->prims.size();
-        for (uint32_t i = a; i < b; i++) out->prims.push_back(items[i].ref);
+        for (uint32_t i = a; i < b; i++) out->prims.push_back(items[i].ref);   // kept for every leaf: the host-side checks walk it
+        if (b - a == 1) {   // the primitive named in the reference itself (BVH_DIRECT): kind << 28 | index
+            const uint32_t pr = items[a].ref;
+            return BVH_LEAF | BVH_DIRECT | ((pr >> 30) << 28) | (pr & 0x0FFFFFFFu);
+        }
         return BVH_LEAF | (off << 3) | (b - a - 1);
     }
     void set_child(uint32_t node, int slot, uint32_t ref, const Box &bx) {
@@ -211,7 +215,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         std::fprintf(stderr, "[bvh] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
         t_prev = t;
     };
-    if ((uint64_t)ns >= (1u << 30) || (uint64_t)nt >= (1u << 30) || (uint64_t)ns + nt >= (1u << 28)) {
+    if ((uint64_t)ns >= (1u << 30) || (uint64_t)nt >= (1u << 30) || (uint64_t)ns + nt >= (1u << 27)) {   // leaf references: 28-bit direct primitive index, 27-bit offset << 3
         err = "bvh: too many primitives";
         return false;
     }

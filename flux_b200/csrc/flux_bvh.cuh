@@ -39,6 +39,8 @@
 
 #define BVH_EMPTY 0xFFFFFFFFu
 #define BVH_LEAF 0x80000000u
+#define BVH_DIRECT 0x40000000u   // leaf of ONE primitive, named in the reference itself: kind << 28 | index (28 bits) — no
+                                 // trip through bvh_prims, one dependent load less per leaf visit
 #define BVH_STACK 32          // entries per thread (shared memory); the builder keeps 3*depth+1 below it
 #define BVH_PAD_REL 1e-7
 #define BVH_PRUNE_REL 1e-9
@@ -272,9 +274,10 @@ struct BvhTraversal {
     __device__ __forceinline__ void leaf(const DevScene &sc, const uint2 *stack, uint32_t stride, unsigned long long *cn) {
         const SphRec *__restrict__ srec = reinterpret_cast<const SphRec *>(sc.bvh_sph);
         const TriRec *__restrict__ trec = reinterpret_cast<const TriRec *>(sc.bvh_tri);
-        const uint32_t off = (cur & 0x7FFFFFFFu) >> 3, cnt = (cur & 7u) + 1u;
+        const bool direct = (cur & BVH_DIRECT) != 0u;
+        const uint32_t off = (cur & 0x3FFFFFFFu) >> 3, cnt = direct ? 1u : (cur & 7u) + 1u;
         for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t pr = __ldg(sc.bvh_prims + off + k);
+            const uint32_t pr = direct ? (((cur >> 28) & 3u) << 30) | (cur & 0x0FFFFFFFu) : __ldg(sc.bvh_prims + off + k);
             const uint32_t idx = pr & 0x3FFFFFFFu;
             double t;
             if ((pr >> 30) == KIND_SPHERE) {
