@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
 // finished takes the next ray of its warp's current chunk at once (ballot rank, no atomics), so the node loop keeps
 // running with most lanes instead of waiting for the warp's longest traversal — ncu on the ray-per-thread form showed
 // 6.9 of 32 lanes per instruction (profiles/r1s_bvh_kernels_full.txt), 9.2 with the refill, 16.1 with bounded runs
-// (profiles/r2h_bvh_kernels_full.txt).  Chunks of TRACE_CHUNK rays come from one global counter (one atomic per chunk),
+// (profiles/r2h_bvh_kernels_full.txt), 18.8 with leaves of one primitive (profiles/r2H_bvh_kernels_full.txt).  Chunks of TRACE_CHUNK rays come from one global counter (one atomic per chunk),
 // so a launch of any size ends with every warp busy until the rays run out: with r1's static split of the batch into
 // equal shares per warp a 4 - 6 M-ray launch spent its last wave half empty.
 #ifndef TRACE_CHUNK
