@@ -56,6 +56,11 @@
 #define TRACE_DESCEND_MAX 8u        // trace_rays_bvh_kernel: lanes refill one by one (4 while leaves held two primitives; with
                                     // leaves of one, r2F: 4 / 6 / 8 = 2496 / 2562 / 2600 Mrays/s)
 #endif
+#ifdef BVH_KEY_NAN_FIRST
+#define BVH_KEY(tn) ((tn) == (tn) ? (tn) : -CUDART_INF_F)   // r1: an unknown entry bound sorts nearest
+#else
+#define BVH_KEY(tn) (tn)
+#endif
 #ifndef BVH_FIRST_LEAF
 #define BVH_FIRST_LEAF 1      // leaf size tried first by the builder (doubled while the tree is too deep for the stack);
                               // measured r1: 2 vs 4 = +8 % on config 5, +1 % on config 3; r2, with bounded descend runs
@@ -246,7 +251,8 @@ struct BvhTraversal {
         /* fmaxf / fminf drop NaN slabs (inf * 0): they constrain nothing; every comparison is false for NaN */    \
         const bool skip = (tn > tf) || (tf < 0.000499f) || (tn > t_prune32);                                       \
         if (skip) ref[k] = BVH_EMPTY;                                                                               \
-        key[k] = ref[k] == BVH_EMPTY ? CUDART_INF_F : (tn == tn ? tn : -CUDART_INF_F);                              \
+        /* a NaN bound (all three slabs NaN) sorts anywhere: the child is still entered or pushed, and never pruned */ \
+        key[k] = ref[k] == BVH_EMPTY ? CUDART_INF_F : BVH_KEY(tn);                                                  \
     }
             BVH_CHILD(0, x) BVH_CHILD(1, y) BVH_CHILD(2, z) BVH_CHILD(3, w)
 #undef BVH_CHILD
