@@ -153,7 +153,7 @@ template <bool COUNT>
 struct BvhTraversal {
     RayCtx r;
     HitRef best;
-    double t_prune, tscale, t_prune_seen;
+    double t_prune, tscale;
     float t_prune32;
     float ia32[3], nlo[3], nhi[3];
     bool pos[3];
@@ -165,6 +165,7 @@ struct BvhTraversal {
         if (COUNT) cn[CN_CANDIDATES]++;
         consider(best, t, id, kind, index);
         t_prune = best.t + BVH_PRUNE_REL * (fabs(best.t) + tscale);
+        t_prune32 = __double2float_ru(t_prune);   // >= t_prune: what the f32 node test prunes against
     }
 
     // pop the nearest stacked subtree that can still hold a closer hit
@@ -190,6 +191,7 @@ struct BvhTraversal {
         // margin scale: one unit of coordinate error moves t by at most 1/|d| <= min_k |1/d_k|
         tscale = sc.bvh_extent * fmin(fabs(r.ia), fmin(fabs(r.ib), fabs(r.ic)));
         t_prune = inf;
+        t_prune32 = CUDART_INF_F;   // >= t_prune, kept in step by candidate()
         for (uint32_t i = 0; i < sc.n_planes; i++) {
             double t;
             if (COUNT) cn[CN_PLANE_TESTS]++;
@@ -220,8 +222,6 @@ struct BvhTraversal {
             nlo[k] = sane ? noa - E : -CUDART_INF_F;   // an axis that cannot be bounded constrains nothing
             nhi[k] = sane ? noa + E : CUDART_INF_F;
         }
-        t_prune32 = CUDART_INF_F;   // >= t_prune, refreshed lazily
-        t_prune_seen = inf;
     }
 
     // inner nodes until this lane holds a leaf or has nothing left — or, with max_steps, for at most that many nodes:
@@ -231,10 +231,6 @@ struct BvhTraversal {
         const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
         for (uint32_t step = 0; !(cur & BVH_LEAF) && step < max_steps; step++) {
             if (COUNT) cn[CN_NODES]++;
-            if (t_prune != t_prune_seen) {
-                t_prune_seen = t_prune;
-                t_prune32 = __double2float_ru(t_prune);
-            }
             const BvhNode4 *nd = nodes + cur;
             const float4 *lo4 = reinterpret_cast<const float4 *>(nd->lo), *hi4 = reinterpret_cast<const float4 *>(nd->hi);
             const float4 ax = __ldg(pos[0] ? lo4 + 0 : hi4 + 0), bx = __ldg(pos[0] ? hi4 + 0 : lo4 + 0);
@@ -250,9 +246,11 @@ struct BvhTraversal {
         const float tf = fminf(fminf(fmaf(bx.C, ia32[0], nhi[0]), fmaf(by.C, ia32[1], nhi[1])), fmaf(bz.C, ia32[2], nhi[2])); \
         /* fmaxf / fminf drop NaN slabs (inf * 0): they constrain nothing; every comparison is false for NaN */    \
         const bool skip = (tn > tf) || (tf < 0.000499f) || (tn > t_prune32);                                       \
+        /* unused slots hold the empty box (+inf, -inf): tn > tf skips them like any missed child.  A NaN bound (all  */ \
+        /* three slabs NaN) sorts anywhere: a real child is still entered or pushed and never pruned, an unused slot  */ \
+        /* keeps its BVH_EMPTY reference and is neither                                                               */ \
         if (skip) ref[k] = BVH_EMPTY;                                                                               \
-        /* a NaN bound (all three slabs NaN) sorts anywhere: the child is still entered or pushed, and never pruned */ \
-        key[k] = ref[k] == BVH_EMPTY ? CUDART_INF_F : BVH_KEY(tn);                                                  \
+        key[k] = skip ? CUDART_INF_F : BVH_KEY(tn);                                                                 \
     }
             BVH_CHILD(0, x) BVH_CHILD(1, y) BVH_CHILD(2, z) BVH_CHILD(3, w)
 #undef BVH_CHILD
