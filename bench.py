@@ -133,26 +133,24 @@ def pick_cpu_root(target_s: float) -> int:
     return int(max(4, min(128, (target_s / per_root1) ** 0.5)))
 
 
-def workload_config(root: int, gpus: int, arm: str = "ours") -> dict:
-    """The workload both arms name, and — separately — what this arm actually rendered per step."""
-    cfg = {"workload": f"scenes/demo2.yml 800x600, max_trace_depth {MAX_DEPTH}, 13 shapes (12 spheres + 1 plane), thin-lens "
-                       "camera; headline = 16384 spp (sample_root 128); metric Msamples/s = W*H*spp / seconds "
-                       "(per-sample cost does not depend on spp)",
-           "sample_root_rendered": root, "spp_rendered": root * root,
-           "samples_per_step": 800 * 600 * root * root}
-    if arm == "ours":
-        cfg.update({
-            "sample_sets": "800 sets x (pixel CMJ, disc CMJ, 5 hemisphere MJ), generated on device, seed 1",
-            "sharding": f"interleaved tiles of {TILE_ROWS} row(s) over {gpus} GPU(s); every GPU stores its pixels into one "
-                        "frame on GPU 0 over NVLink peer memory (no gather collective)",
-            "l2": f"sample sets {800 * root * root * (32 + 24 * MAX_DEPTH) / 1e6:.0f} MB per GPU "
-                  f"{'exceed' if 800 * root * root * (32 + 24 * MAX_DEPTH) > 126e6 else 'fit in'} the 126 MB L2; "
-                  "no cross-step reuse of outputs"})
-    else:
-        cfg.update({"sample_sets": "800 sets generated by the oracle's CPU generator, seed 1",
-                    "note": f"the CPU arm renders the full 800x600 frame at sample_root {root} ({root * root} spp) per step — a bounded "
-                            "sample of the 16384-spp workload; Msamples/s is spp-independent"})
-    return cfg
+def workload_config(gpus: int) -> dict:
+    """The workload, named identically by both arms (the driver compares the two `config` objects); what an arm actually
+    rendered per step is its line's `ran` object and, for the CPU arm, `cpu_baseline.sample`."""
+    root = 128
+    return {"workload": f"scenes/demo2.yml 800x600 at 16384 spp (sample_root 128), max_trace_depth {MAX_DEPTH}, 13 shapes (12 spheres + "
+                        "1 plane), thin-lens camera; metric Msamples/s = W*H*spp / seconds",
+            "sample_bound": "our arm renders the whole 16384-spp frame every step; the reference (CPU) arm renders the whole frame at a "
+                            "bounded sample count per step — per-sample cost does not depend on spp — and both lines say what they "
+                            "ran under `ran`",
+            "sample_sets": "800 sets x (pixel CMJ, disc CMJ, 5 hemisphere MJ), seed 1 (ours: generated on the device; CPU arm: by the oracle)",
+            "sharding": f"ours: interleaved tiles of {TILE_ROWS} row(s) over {gpus} GPU(s); every GPU stores its pixels into one frame on "
+                        "GPU 0 over NVLink peer memory (no gather collective)",
+            "l2": f"sample sets {800 * root * root * (32 + 24 * MAX_DEPTH) / 1e6:.0f} MB per GPU exceed the 126 MB L2; no cross-step "
+                  "reuse of outputs"}
+
+
+def ran(root: int, what: str) -> dict:
+    return {"sample_root": root, "spp": root * root, "samples_per_step": 800 * 600 * root * root, "what": what}
 
 
 def run_reference_arm(args):
@@ -176,7 +174,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "demo2.yml render throughput", "value": msps, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": msps / 5.314, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(root, args.gpus, "reference"),
+        "config": workload_config(args.gpus),
+        "ran": ran(root, "CPU oracle, full 800x600 frame per step at this sample count (a bounded sample of the 16384-spp workload)"),
         "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
                          "region": "render only (a); sample sets generated before the clock starts",
                          "value_render_plus_sample_generation": msps_b,
@@ -670,7 +669,8 @@ def main():
             "metric": "demo2.yml render throughput", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": value / 5.314, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(root, world), "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(world), "ran": ran(root, "the whole frame on the GPU(s), every step"), "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "frame_sha256": frame_sha256, "frame_assembly": assembly_note or args.gather,
             "kernel_ms_max_over_ranks": kernel_ms_max, "kernel_ms_min_over_ranks": kernel_ms_min,

@@ -67,3 +67,18 @@ def test_ppm_writer_matches_image_rs(tmp_path):
     p = tmp_path / "x.ppm"
     assert _capi.lib().flux_write_ppm(str(p).encode(), 2, 1, _capi.as_dp(rgb)) == 0
     assert p.read_text() == "P3\n2 1\n65535\n0 32767 65535\n65535 0 0\n"  # image.rs:45-52
+
+
+def test_frame_entry_points_refuse_null_arguments_without_a_device():
+    """flux_frame_* / flux_ctx_sync check their arguments before they touch CUDA (no GPU here)."""
+    lib = _capi.lib()
+    out = ctypes.c_void_p()
+    assert lib.flux_frame_create(None, 8, 8, ctypes.byref(out)) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_open_ipc(None, bytes(64), 8, 8, ctypes.byref(out)) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_open_peer(None, None, ctypes.byref(out)) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_export(None, ctypes.create_string_buffer(64)) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_read(None, None) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_device_ptr(None, ctypes.byref(out)) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_frame_close(None) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_ctx_sync(None) == _capi.FLUX_ERR_INVALID
+    assert lib.flux_render_row_list_into_frame(None, None, 0, None, None) == _capi.FLUX_ERR_INVALID
