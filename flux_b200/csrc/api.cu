@@ -878,6 +878,8 @@ int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_
     p.out = nullptr;
     p.counters = ctx->counters.p;
     p.work_counter = ctx->work_counter.p;
+    std::memcpy(p.cull, ctx->cull, sizeof(p.cull));   // the direct kernel classifies sphere boxes in FP32 too (flux_cull.cuh)
+    p.cull_cmax = ctx->cull_cmax;
     p.i_begin = sample_begin;
     p.i_end = sample_end;
     p.accum = ctx->accum.p;

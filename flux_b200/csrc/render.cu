@@ -12,6 +12,7 @@
 // xor-shuffle tree, so the result does not depend on grid size, scheduling or
 // the number of GPUs.
 #include "flux_bvh.cuh"
+#include "flux_cull.cuh"
 #include "flux_intersect.cuh"
 #include "flux_kernels.cuh"
 #include "flux_shade.cuh"
@@ -29,7 +30,7 @@ __device__ __forceinline__ void primary_ray(const DevCamera &cam, uint32_t row, 
     double lpy = ds.y * cam.lens_radius;
     double px2 = u * cam.factor;
     double py2 = v * cam.factor;
-    d = normalize3(((px2 - lpx) * cam.u + (py2 - lpy) * cam.v) - cam.focal_w);
+    d = normalize3_dev(((px2 - lpx) * cam.u + (py2 - lpy) * cam.v) - cam.focal_w);   // = normalize3, one shared reciprocal (flux_math.cuh)
     o = (cam.eye + lpx * cam.u) + lpy * cam.v;
 }
 
@@ -42,6 +43,7 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
     Rgb L;
     uint32_t depth = 1;
     const DevScene &sc = p.scene;
+    const bool culled = sc.n_tris == 0 && sc.n_spheres <= FLUX_CULL_MAX;   // uniform
     for (;;) {
         if (depth > p.cam.max_depth) {  // scene.rs:164-165
             if (COUNT) cn[CN_DEPTH_CUT]++;
@@ -49,8 +51,16 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
             break;
         }
         if (COUNT) cn[CN_SEGMENTS]++;
-        RayCtx r = make_ray(o, d);
-        HitRef h = BVH ? closest_hit_bvh<COUNT>(sc, r, stack, blockDim.x, cn) : closest_hit_linear<COUNT>(sc, r, cn);
+        RayCtx r;
+        HitRef h;
+        if (!BVH && culled) {   // spheres and planes only: FP32-classified boxes (flux_cull.cuh); the hit record needs o and d only
+            r.o = o;
+            r.d = d;
+            h = closest_hit_linear_culled<COUNT>(p, o, d, cn);
+        } else {
+            r = make_ray(o, d);
+            h = BVH ? closest_hit_bvh<COUNT>(sc, r, stack, blockDim.x, cn) : closest_hit_linear<COUNT>(sc, r, cn);
+        }
         if (h.shape_id == 0xFFFFFFFFu) {  // scene.rs:168
             if (COUNT) cn[CN_MISS]++;
             L = Rgb{p.cam.bg[0], p.cam.bg[1], p.cam.bg[2]};
@@ -106,8 +116,12 @@ __device__ __forceinline__ Rgb trace_path(const RenderParams &p, V3 o, V3 d, uin
     return L;
 }
 
+#ifndef RENDER_MIN_BLOCKS
+#define RENDER_MIN_BLOCKS 4   // linear-scan instantiations only (the BVH ones keep the compiler's own 113 registers).  Config 1,
+                              // r2S/r2T: 1 / 2 / 3 / 4 blocks = 4425 / 4526 / 5060-5093 / 5423 Msamples/s (round 1 kernel: 4136)
+#endif
 template <bool COUNT, bool BVH>
-__global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ RenderParams p, uint32_t G) {
+__global__ void __launch_bounds__(256, BVH ? 1 : RENDER_MIN_BLOCKS) render_kernel(const __grid_constant__ RenderParams p, uint32_t G) {
     extern __shared__ uint2 bvh_stack[];  // [BVH_STACK][blockDim.x] when BVH
     uint2 *stack = BVH ? bvh_stack + threadIdx.x : nullptr;
     const uint32_t lane = threadIdx.x & 31u;
