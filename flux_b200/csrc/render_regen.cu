@@ -22,6 +22,7 @@
 // memory as AoS records; bounding-box corners are addressed through per-ray
 // near/far offsets so the slab test needs no selects.
 #include "flux_bvh.cuh"
+#include "flux_cull.cuh"
 #include "flux_intersect.cuh"
 #include "flux_kernels.cuh"
 #include "flux_shade.cuh"
@@ -35,6 +36,10 @@
 #endif
 #ifndef REGEN_TWO_PHASE
 #define REGEN_TWO_PHASE 1
+#endif
+#ifndef REGEN_CULL32
+#define REGEN_CULL32 1   // phase 1 classifies the sphere boxes in FP32 (conservative; exact f64 test where undecided), as the
+                         // wavefront and the direct kernel do (flux_cull.cuh): round 1 ran 12 f64 slab products per sphere
 #endif
 
 namespace {
@@ -73,17 +78,64 @@ __host__ __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return
 //      instead of once per sphere that any lane's box test passed (v1: the quadratic ran for 85 % of
 //      all spheres per warp with 11 of 32 lanes active; profiles/r1b_render_regen_full.txt).
 template <bool COUNT>
-__device__ __forceinline__ void closest_hit_smem(const SmemScene &sc, V3 o, V3 d, double &best_t, uint32_t &best_id,
+__device__ __forceinline__ void closest_hit_smem(const RenderParams &p, const SmemScene &sc, V3 o, V3 d, double &best_t, uint32_t &best_id,
                                                  uint32_t &best_ref, unsigned long long *cn) {
-    // ray-invariant terms (shapes.rs:107-122,177,180,187), hoisted
-    const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
-    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
     const double A = dot3(d, d);
     const double A2 = 2.0 * A, A4 = 4.0 * A;
     best_t = 0.0;
     best_id = 0xFFFFFFFFu;
     best_ref = 0;
-#if REGEN_TWO_PHASE
+#if REGEN_TWO_PHASE && REGEN_CULL32
+    // ---- phase 1: conservative FP32 classification of every sphere box (constant-bank operands), exact test where undecided ----
+    unsigned long long mask = 0ull;
+    {
+        const LinCullRay c = lin_cull_ray(p, o, d);
+#pragma unroll 1
+        for (uint32_t base = 0; base < sc.ns; base += 32u) {
+            const uint32_t nsb = sc.ns - base < 32u ? sc.ns - base : 32u;
+            uint32_t okm = 0u, failm = 0u;
+#pragma unroll 2
+            for (uint32_t j = 0; j < nsb; j++) {
+                const uint32_t i = base + j;
+                const float r = p.cull[i][3];
+                const float tcx = fmaf(p.cull[i][0], c.iax, c.nox);
+                const float tcy = fmaf(p.cull[i][1], c.iay, c.noy);
+                const float tcz = fmaf(p.cull[i][2], c.iaz, c.noz);
+                const float tn = fmaxf(fmaxf(fmaf(-r, c.aax, tcx), fmaf(-r, c.aay, tcy)), fmaxf(fmaf(-r, c.aaz, tcz), (float)FLUX_T_MIN));
+                const float tf = fminf(fminf(fmaf(r, c.aax, tcx), fmaf(r, c.aay, tcy)), fmaf(r, c.aaz, tcz));
+                const float sgap = tf - tn;
+                if (sgap > c.e2) okm |= 1u << j;
+                if (sgap < -c.e2) failm |= 1u << j;
+            }
+            const uint32_t valid = nsb >= 32u ? ~0u : ((1u << nsb) - 1u);
+            uint32_t m32 = okm & valid;
+            uint32_t unc = ~(okm | failm) & valid;
+            if (unc) {   // the exact BoundingBox::hit (shapes.rs:98-133); its reciprocals are formed on this rare path only
+                const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
+                const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
+                while (unc) {
+                    const uint32_t j = (uint32_t)__ffs((int)unc) - 1u;
+                    unc &= unc - 1u;
+                    const double *s = sc.sph + (size_t)(base + j) * R_SPH_STRIDE;
+                    const double tx_min = (s[R_C0X + sx] - o.x) * ia, tx_max = (s[R_C1X - sx] - o.x) * ia;
+                    const double ty_min = (s[R_C0Y + sy] - o.y) * ib, ty_max = (s[R_C1Y - sy] - o.y) * ib;
+                    const double tz_min = (s[R_C0Z + sz] - o.z) * ic, tz_max = (s[R_C1Z - sz] - o.z) * ic;
+                    const double t0 = ref_max(tx_min, ref_max(ty_min, tz_min));
+                    const double t1 = ref_min(tx_max, ref_min(ty_max, tz_max));
+                    if (t0 < t1 && t1 > FLUX_T_MIN) m32 |= 1u << j;
+                }
+            }
+            mask |= (unsigned long long)m32 << base;
+        }
+        if (COUNT) {
+            cn[CN_BBOX_TESTS] += sc.ns;
+            cn[CN_BBOX_PASS] += __popcll(mask);
+        }
+    }
+#elif REGEN_TWO_PHASE
+    // ray-invariant terms (shapes.rs:107-122), hoisted
+    const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
+    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
     // ---- phase 1: slab tests ----
     unsigned long long mask = 0ull;
     {
@@ -103,6 +155,8 @@ __device__ __forceinline__ void closest_hit_smem(const SmemScene &sc, V3 o, V3 d
             cn[CN_BBOX_PASS] += __popcll(mask);
         }
     }
+#endif
+#if REGEN_TWO_PHASE
     // ---- phase 2: quadratics of the lanes' own candidates, in increasing shape order ----
     while (mask != 0ull) {  // SIMT: the warp iterates max-over-lanes(popcount(mask)) times
         const uint32_t i = (uint32_t)__ffsll((long long)mask) - 1u;
@@ -130,6 +184,8 @@ __device__ __forceinline__ void closest_hit_smem(const SmemScene &sc, V3 o, V3 d
         }
     }
 #else
+    const double ia = 1.0 / d.x, ib = 1.0 / d.y, ic = 1.0 / d.z;
+    const int sx = ia >= 0.0 ? 0 : 1, sy = ib >= 0.0 ? 0 : 1, sz = ic >= 0.0 ? 0 : 1;
     const double *s = sc.sph;
 #pragma unroll 2
     for (uint32_t i = 0; i < sc.ns; i++, s += R_SPH_STRIDE) {
@@ -303,7 +359,7 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                     hid = href_bvh.shape_id;
                     t = href_bvh.t;
                 } else {
-                    closest_hit_smem<COUNT>(sc, o, d, t, hid, href, cn);
+                    closest_hit_smem<COUNT>(p, sc, o, d, t, hid, href, cn);
                 }
                 if (hid == 0xFFFFFFFFu) {  // scene.rs:168
                     if (COUNT) cn[CN_MISS]++;
