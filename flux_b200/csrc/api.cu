@@ -428,6 +428,7 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         sc.bvh_tri = ctx->bvh_tri.p;
         sc.bvh_linear = ctx->bvh_linear.p;
         sc.bvh_n_linear = (uint32_t)bb.linear.size();
+        sc.bvh_tree_spheres = ns - (uint32_t)bb.linear.size();
         sc.bvh_extent = bb.extent;
         ctx->bvh_depth = bb.depth;
         ctx->bvh_leaf = bb.leaf_size;

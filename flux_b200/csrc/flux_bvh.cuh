@@ -149,7 +149,10 @@ __device__ __forceinline__ bool tri_t_rec(const RayCtx &r, const TriRec *__restr
 // "while-while" order: descend() keeps a lane on inner nodes until it holds a leaf (or is done) before leaf() runs the
 // f64 primitive tests, so the two very different code paths each execute with most of the warp (ncu on an if/else
 // loop: 6.9 of 32 lanes per instruction on incoherent rays, profiles/r1s_bvh_kernels_full.txt).
-template <bool COUNT>
+// SPH = false: the tree holds no sphere (every sphere of the scene, if any, is on the linear list handled in begin()),
+// so after begin() the ray's reciprocals and d.d terms are dead and the leaf code is the triangle test alone — fewer
+// live registers in kernels that spill (the render kernels on mesh scenes).
+template <bool COUNT, bool SPH = true>
 struct BvhTraversal {
     RayCtx r;
     HitRef best;
@@ -284,7 +287,7 @@ struct BvhTraversal {
             const uint32_t pr = direct ? (((cur >> 28) & 3u) << 30) | (cur & 0x0FFFFFFFu) : __ldg(sc.bvh_prims + off + k);
             const uint32_t idx = pr & 0x3FFFFFFFu;
             double t;
-            if ((pr >> 30) == KIND_SPHERE) {
+            if (SPH && (pr >> 30) == KIND_SPHERE) {
                 const SphRec *s = srec + idx;
                 if (sphere_t_rec<COUNT>(r, s, t, cn)) candidate(t, __ldg(&s->shape_id), KIND_SPHERE, idx, cn);
             } else {
@@ -297,10 +300,10 @@ struct BvhTraversal {
     }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool SPH = true>
 __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayCtx &r, uint2 *stack, uint32_t stride,
                                                   unsigned long long *cn) {
-    BvhTraversal<COUNT> T;
+    BvhTraversal<COUNT, SPH> T;
     T.begin(sc, r, cn);
     while (!T.done()) {
         T.descend(sc, stack, stride, cn, BVH_DESCEND_MAX);

@@ -57,6 +57,7 @@ struct DevScene {
     uint32_t bvh_n_linear;
     uint32_t bvh_n_nodes;
     uint32_t use_bvh;
+    uint32_t bvh_tree_spheres;  // spheres inside the tree (0: only triangles there; the spheres, if any, are on the linear list)
     double bvh_extent;          // max |coordinate| of the boxes in the tree (scale of the pruning margin)
 };
 

@@ -37,6 +37,9 @@
 #ifndef REGEN_TWO_PHASE
 #define REGEN_TWO_PHASE 1
 #endif
+#ifndef REGEN_TRI_ONLY
+#define REGEN_TRI_ONLY 1   // mesh scenes whose tree holds no sphere run the triangle-only traversal instantiation
+#endif
 #ifndef REGEN_CULL32
 #define REGEN_CULL32 1   // phase 1 classifies the sphere boxes in FP32 (conservative; exact f64 test where undecided), as the
                          // wavefront and the direct kernel do (flux_cull.cuh): round 1 ran 12 f64 slab products per sphere
@@ -240,7 +243,8 @@ __device__ __forceinline__ void closest_hit_smem(const RenderParams &p, const Sm
 
 // BVH = true: closest hit through the 4-wide BVH over the scene in global memory (meshes, many spheres) instead of
 // the shared-memory linear scan; shared memory then holds the per-thread traversal stacks.
-template <bool COUNT, bool BVH>
+// TRI: BVH scenes whose tree holds triangles only (DevScene::bvh_tree_spheres == 0; BvhTraversal<·, false>).
+template <bool COUNT, bool BVH, bool TRI = false>
 __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2 *bvh_stack = reinterpret_cast<uint2 *>(smem_raw) + threadIdx.x;   // [BVH_STACK][blockDim.x] when BVH
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(REGEN_THREADS, REGEN_MIN_BLOCKS) render_regen_
                 HitRef href_bvh;
                 if (BVH) {
                     rc = make_ray(o, d);
-                    href_bvh = closest_hit_bvh<COUNT>(p.scene, rc, bvh_stack, blockDim.x, cn);
+                    href_bvh = closest_hit_bvh<COUNT, !TRI>(p.scene, rc, bvh_stack, blockDim.x, cn);
                     hid = href_bvh.shape_id;
                     t = href_bvh.t;
                 } else {
@@ -506,11 +510,14 @@ void launch_render_regen(const RenderParams &p, bool count, int sm_count, cudaSt
         kern<<<blocks, threads, smem, stream>>>(p);
     };
     const bool bvh = p.scene.use_bvh != 0;
+    const bool tri = bvh && p.scene.bvh_tree_spheres == 0 && REGEN_TRI_ONLY;
     if (count) {
-        if (bvh) go(render_regen_kernel<true, true>);
+        if (tri) go(render_regen_kernel<true, true, true>);
+        else if (bvh) go(render_regen_kernel<true, true>);
         else go(render_regen_kernel<true, false>);
     } else {
-        if (bvh) go(render_regen_kernel<false, true>);
+        if (tri) go(render_regen_kernel<false, true, true>);
+        else if (bvh) go(render_regen_kernel<false, true>);
         else go(render_regen_kernel<false, false>);
     }
 }
