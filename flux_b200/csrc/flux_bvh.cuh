@@ -50,7 +50,8 @@
 // config 5, 20 M rays: unbounded 1841, 1 / 2 / 3 / 4 / 5 nodes 1690 / 2030 / 2175 / 2314 / 2245 Mrays/s;
 // config 3 (regeneration kernel): unbounded 633, 1 / 2 / 3 / 4 / 5 nodes 639 / 675 / 670 / 659 / 653 Msamples/s.
 #ifndef BVH_DESCEND_MAX
-#define BVH_DESCEND_MAX 2u          // closest_hit_bvh: the render kernels (a warp's lanes start their segments together)
+#define BVH_DESCEND_MAX 1u          // closest_hit_bvh: the render kernels (a warp's lanes start their segments together); 2 until the
+                                    // triangle-only instantiation: with it 1 / 2 / 3 = 908 / 893 / 865 Msamples/s on config 3 (r2W)
 #endif
 #ifndef TRACE_DESCEND_MAX
 #define TRACE_DESCEND_MAX 8u        // trace_rays_bvh_kernel: lanes refill one by one (4 while leaves held two primitives; with
