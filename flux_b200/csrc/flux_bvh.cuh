@@ -178,7 +178,13 @@ struct BvhTraversal {
         while (sp) {
             sp--;
             const uint2 e = stack[(size_t)sp * stride];
+#ifdef BVH_POP_F64
             if ((double)__uint_as_float(e.y) > t_prune) continue;   // became prunable since it was pushed
+#else
+            // became prunable since it was pushed?  Against the f32 bound (>= t_prune: never prunes what f64 would keep):
+            // no conversion to double on the XU pipe in a loop that runs at 3 - 5 lanes (9 % of config 3's issue slots)
+            if (__uint_as_float(e.y) > t_prune32) continue;
+#endif
             cur = e.x;
             break;
         }
