@@ -205,3 +205,27 @@ def test_bvh_builder_names_the_first_triangle_with_a_non_finite_vertex():
         flat = SceneData("bad", sd.output_settings, sd.background, list(sd.shapes) + extra, sd.camera_settings, sd.camera_data).flatten()
         assert _capi.lib().flux_bvh_describe(flat.ptr(), out) != 0
         assert _capi.lib().flux_last_error(None).decode() == f"bvh: triangle {first} has a non-finite vertex"
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_zero():
+    """The driver launches `bench.py --impl reference` the way it launches our arm — under torchrun for N > 1.  Rank 0
+    alone runs the CPU oracle and prints the one JSON line; the other ranks exit 0 without work.  Both arms print the
+    same `config` object; what this arm rendered per step is under `ran`."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--cpu-root", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "Msamples/s" and d["higher_is_better"] is True
+    assert d["ran"]["sample_root"] == 3 and d["ran"]["spp"] == 9
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.workload_config(2)   # the very object our arm prints at 2 GPUs
