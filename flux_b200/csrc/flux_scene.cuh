@@ -73,7 +73,10 @@ struct DevSamples {
 };
 
 #define FLUX_CULL_MAX 128  // spheres covered by the constant-bank FP32 table (render_wave2.cu)
-#define FLUX_WAVE2_LINEAR_MAX 112  // up to here render_wave2.cu scans linearly even when a BVH exists (api.cu)
+#ifndef FLUX_WAVE2_LINEAR_MAX
+#define FLUX_WAVE2_LINEAR_MAX 128  // up to here render_wave2.cu scans linearly even when a BVH exists (api.cu); 112 in r1, when the two
+                                   // met at ~120 spheres; with the primary mask the linear scan leads at 124: 2639 vs 2375 Msamples/s (r2AJ)
+#endif
 
 struct RenderParams {
     DevScene scene;
