@@ -52,6 +52,7 @@ struct flux_ctx {
     std::string err;
 
     bool have_scene = false, have_samples = false, have_index = false;
+    bool samples_in_range = true;   // pixel samples in [0,1]^2, lens samples in the unit disc (RenderParams::primary_mask_ok)
     // what the set-index map on the device was validated (flux_set_set_index) or generated for: it is usable only
     // while the image size and the number of sample sets are still these (index_valid)
     uint32_t idx_W = 0, idx_H = 0, idx_sets = 0;
@@ -518,6 +519,16 @@ int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t 
     int rc = alloc_samples(ctx, root, max_depth, num_sets);
     if (rc) return rc;
     const size_t n = (size_t)root * root;
+    {   // the reference's sets are unit-square / unit-disc samples (samplers/src/lib.rs:46-131); a caller may hand over
+        // anything, and the wavefront kernel's per-pixel primary mask must then stand aside
+        bool ok = true;
+        const size_t m = n * num_sets;
+        for (size_t k = 0; k < m && ok; k++) {
+            const double px = pixel_xy[2 * k], py = pixel_xy[2 * k + 1], dx = disc_xy[2 * k], dy = disc_xy[2 * k + 1];
+            ok = px >= 0.0 && px <= 1.0 && py >= 0.0 && py <= 1.0 && dx * dx + dy * dy <= 1.0 + 1e-12;
+        }
+        ctx->samples_in_range = ok;
+    }
     CK(cudaMemcpyAsync(ctx->pixel.p, pixel_xy, n * num_sets * 16, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->disc.p, disc_xy, n * num_sets * 16, cudaMemcpyHostToDevice, ctx->stream));
     if (max_depth) CK(cudaMemcpyAsync(ctx->hemi.p, hemi_xyz, n * num_sets * max_depth * 24, cudaMemcpyHostToDevice, ctx->stream));
@@ -543,6 +554,7 @@ int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
     if (rc) return rc;
     CK(ctx->set_index.reserve((size_t)ctx->cam.W * ctx->cam.H));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->samples_in_range = true;   // by construction (samplegen.cu)
     launch_generate_samples(seed, root, depth, num_sets, ctx->pixel.p, ctx->disc.p, ctx->hemi.p, ctx->stream);
     launch_generate_set_index(seed, ctx->cam.H, ctx->cam.W, num_sets, ctx->set_index.p, ctx->stream);
     ctx->launches += 2;
@@ -644,6 +656,7 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     p.work_counter = ctx->work_counter.p;
     std::memcpy(p.cull, ctx->cull, sizeof(p.cull));
     p.cull_cmax = ctx->cull_cmax;
+    p.primary_mask_ok = ctx->samples_in_range ? 1u : 0u;
     p.i_begin = 0;
     p.i_end = ctx->ss.n;
     p.accum = nullptr;
@@ -881,6 +894,7 @@ int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_
     p.work_counter = ctx->work_counter.p;
     std::memcpy(p.cull, ctx->cull, sizeof(p.cull));   // the direct kernel classifies sphere boxes in FP32 too (flux_cull.cuh)
     p.cull_cmax = ctx->cull_cmax;
+    p.primary_mask_ok = ctx->samples_in_range ? 1u : 0u;
     p.i_begin = sample_begin;
     p.i_end = sample_end;
     p.accum = ctx->accum.p;

@@ -94,6 +94,9 @@ struct RenderParams {
     // non-finite) and for the unused entries.  cull_cmax >= max_k |centre_k| + radius over the valid spheres.
     float cull[FLUX_CULL_MAX][4];
     float cull_cmax;
+    // 1: pixel samples lie in [0,1]^2 and lens samples in the unit disc (always so for device-generated sets; checked on
+    // upload for caller-supplied ones) — what the per-pixel primary-ray mask of render_wave2.cu is derived from
+    uint32_t primary_mask_ok;
     // progressive passes (flux_progressive_pass, render.cu only): samples [i_begin, i_end) of every pixel; when
     // `accum` is set their radiance sum is added to accum[n_rows][W][3] instead of being averaged into `out`
     uint32_t i_begin, i_end;

@@ -409,7 +409,8 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
             bool may = false;
             if (tid < ns) {
                 const double *s = w.sph + (size_t)tid * V_SPH_STRIDE;
-                may = primary_may_hit(cam, colf, rowf, s[V_CX], s[V_CY], s[V_CZ], s[V_RB]);
+                // caller-supplied sample sets outside the unit square / disc void the bound: then every box stays in the mask
+                may = p.primary_mask_ok ? primary_may_hit(cam, colf, rowf, s[V_CX], s[V_CY], s[V_CZ], s[V_RB]) : true;
             }
             const uint32_t b = __ballot_sync(0xffffffffu, may);
             if (lane == 0 && warp < FLUX_CULL_MAX / 32) s_pm[warp] = b;

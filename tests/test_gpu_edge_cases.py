@@ -222,3 +222,28 @@ def test_stale_set_index_map_is_refused(gpu_ctx):
     gpu_ctx.set_set_index(np.zeros((10, 20), np.uint32))
     img = gpu_ctx.render_rows(0, 9, 20)
     assert np.isfinite(img).all()
+
+
+def test_caller_samples_outside_the_unit_square_switch_the_primary_mask_off(gpu_ctx, demo2):
+    """The per-pixel primary-ray mask of the wavefront kernel is derived from unit-square pixel samples and unit-disc
+    lens samples.  Caller-supplied sets may be anything (flux_set_samples): with samples three pixels wide and a lens
+    disc of radius 2 the camera rays leave the pixel's bundle, the mask must stand aside, and the image still equals the
+    oracle's on the same sets."""
+    sd = demo2.with_size(20, 14)
+    cfg = JobConfiguration(16, 5, 50)
+    flat = sd.flatten()
+    ss = Hp.oracle_samples(77, cfg, 20, 14)
+    ss.pixel = ss.pixel * 3.0 - 1.0      # [-1, 2): three pixels wide
+    ss.disc = ss.disc * 2.0              # lens samples out to radius 2
+    Hp.upload(gpu_ctx, flat, cfg, ss)
+    try:
+        gpu_ctx.set_kernel_mode(4)
+        img = gpu_ctx.render_rows(0, 13, 20)
+        gpu_ctx.enable_counters(True)
+        counted = gpu_ctx.render_rows(0, 13, 20)
+    finally:
+        gpu_ctx.enable_counters(False)
+        gpu_ctx.set_kernel_mode(0)
+    ref = O.render_rows(flat, cfg, ss, 0, 13)
+    assert Hp.rel_err(img, ref) <= 1e-6
+    assert np.array_equal(img.view(np.uint64), counted.view(np.uint64))
