@@ -192,7 +192,7 @@ V3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
 
 extern "C" {
 
-const char *flux_version(void) { return "fluxb200 0.1.0 (sm_100a)"; }
+const char *flux_version(void) { return "fluxb200 0.2.0 (sm_100a)"; }
 
 const char *flux_last_error(const flux_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
