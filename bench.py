@@ -317,7 +317,8 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
         out["roofline"] = {"bound": "fp64_pipe", "achieved": ach, "peak": env.peak_ginstr / 1e3, "unit": "TFLOP/s",
                            "frac": ach / (env.peak_ginstr / 1e3), "ops_per_sample": ops / n_samples, "traffic": None,
                            "note": "per GPU; algorithmic FP64 ops (SURVEY.md §8d model x event counters of every "
-                                   f"{counter_stride}th row) / max-over-ranks kernel time vs the live FP64 issue rate"}
+                                   f"{counter_stride}th row) / max-over-ranks kernel time vs the live FP64 issue rate",
+                           "ncu": _ncu_note("render_kernel_c1") if root * root < 64 else _ncu_note("render_wave2")}
     else:
         seg = max(1.0, tot["segments"])
         bps = (tot["nodes_visited"] * 128 + tot["bbox_tests"] * 112 + tot["tri_tests"] * 96) / seg
