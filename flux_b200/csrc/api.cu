@@ -991,6 +991,10 @@ int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d,
         CK(cudaEventCreateWithFlags(&ev.v[k], timing ? cudaEventDefault : cudaEventDisableTiming));
     }
     cudaEvent_t *freed = ev.v.data() + 3 * n_pieces;
+    struct Drain {   // an error return must not leave copies to or from the caller's buffers in flight
+        flux_ctx *c;
+        ~Drain() { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); cudaGetLastError(); }
+    } drain{ctx};
     for (uint64_t k = 0; k < n_pieces; k++) {
         const uint64_t off = k * piece, c = std::min(piece, n - off);
         const int b = (int)(k % nb);
