@@ -83,6 +83,7 @@ struct flux_ctx {
     DevBuf<unsigned long long> trace_work;   // chunk counter of the ray-batch kernel
     // BVH extension (flux_bvh.cuh)
     DevBuf<BvhNode4> bvh_nodes;
+    cudaTextureObject_t bvh_tex = 0;   // bvh_nodes as a linear uint4 texture (DevScene::bvh_tex)
     DevBuf<SphRec> bvh_sph;
     DevBuf<TriRec> bvh_tri;
     DevBuf<uint32_t> bvh_prims, bvh_linear;
@@ -102,6 +103,7 @@ struct flux_ctx {
         ray_hit.release(); materials.release(); pixel.release(); disc.release(); counters.release();
         work_counter.release(); trace_work.release(); bvh_nodes.release(); bvh_sph.release(); bvh_tri.release(); bvh_prims.release();
         bvh_linear.release();
+        if (bvh_tex) cudaDestroyTextureObject(bvh_tex);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (s_in) cudaStreamDestroy(s_in);
@@ -421,8 +423,26 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         CK(up(ctx->bvh_prims.p, bb.prims.data(), bb.prims.size() * sizeof(uint32_t)));
         CK(up(ctx->bvh_linear.p, bb.linear.data(), bb.linear.size() * sizeof(uint32_t)));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->bvh_tex) {
+            cudaDestroyTextureObject(ctx->bvh_tex);
+            ctx->bvh_tex = 0;
+        }
+        {   // the nodes once more as a linear texture: eight uint4 texels per node
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = ctx->bvh_nodes.p;
+            rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindUnsigned);
+            rd.res.linear.sizeInBytes = bb.nodes.size() * sizeof(BvhNode4);
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&ctx->bvh_tex, &rd, &td, nullptr) != cudaSuccess) {
+                ctx->bvh_tex = 0;
+                cudaGetLastError();
+            }
+        }
         sc.use_bvh = 1;
         sc.bvh_nodes = ctx->bvh_nodes.p;
+        sc.bvh_tex = (unsigned long long)ctx->bvh_tex;
         sc.bvh_n_nodes = (uint32_t)bb.nodes.size();
         sc.bvh_prims = ctx->bvh_prims.p;
         sc.bvh_sph = ctx->bvh_sph.p;

@@ -93,6 +93,26 @@ struct __align__(16) TriRec {   // 80 B... padded to 96
 #ifdef __CUDACC__
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
+// Node fetches of the ray-batch kernel are split between the two data paths of the SM's L1: bit k of the mask sends
+// fetch k (near x, far x, near y, far y, near z, far z, children; 16 bytes each) through the texture unit, the rest
+// through the LSU.  ncu on config 5 (r2H): the kernel sat at 91 % of l1tex__data_pipe_lsu_wavefronts with issue slots
+// 37 % busy — an incoherent 16-byte load costs the LSU data pipe one wavefront per LANE, seven of them per lane and node —
+// and one more resident CTA per SM changed nothing.  Measured on one B200, 20 M rays: all seven through the LSU 2698
+// Mrays/s, all through the texture unit 2890, split 3 + 4 (mask 7) 3419, 4 + 3 (mask 15) 3442, near x / far x / near y +
+// children (71) 3452.  (Three 256-bit LDG.E.256 loads at fixed offsets with near / far picked in registers: 2914 — the
+// requests fall by 36 % but the data-pipe wavefronts only by 9 %.)  The render kernels keep every fetch on the LSU
+// (mask 0, the r1 code): config 3 with any mask 862 - 890 against 934 Msamples/s — their L1 hit rate is 51 %, an L1 hit
+// is quick through the LSU and as slow as a miss through the texture pipe, and they are issue-bound as much as L1-bound.
+#ifndef TRACE_TEX_MASK
+#define TRACE_TEX_MASK 71
+#endif
+#ifndef BVH_TEX_MASK
+#define BVH_TEX_MASK 0
+#endif
+__device__ __forceinline__ float4 u4f(uint4 v) {
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
 // Sphere::hit distance on a leaf record (same expressions as sphere_t in flux_intersect.cuh).
 template <bool COUNT>
 __device__ __forceinline__ bool sphere_t_rec(const RayCtx &r, const SphRec *__restrict__ s, double &t_out,
@@ -236,17 +256,34 @@ struct BvhTraversal {
 
     // inner nodes until this lane holds a leaf or has nothing left — or, with max_steps, for at most that many nodes:
     // the lane may then still hold an inner node (no leaf bit) and goes on in the caller's next round
+    // TEXM: which of the seven 16-byte fetches of a node go through the texture unit (TRACE_TEX_MASK above); needs
+    // sc.bvh_tex.  0 = all through the LSU.
+    template <int TEXM = BVH_TEX_MASK>
     __device__ __forceinline__ void descend(const DevScene &sc, uint2 *stack, uint32_t stride, unsigned long long *cn,
                                             uint32_t max_steps = 0xFFFFFFFFu) {
         const BvhNode4 *__restrict__ nodes = reinterpret_cast<const BvhNode4 *>(sc.bvh_nodes);
         for (uint32_t step = 0; !(cur & BVH_LEAF) && step < max_steps; step++) {
             if (COUNT) cn[CN_NODES]++;
             const BvhNode4 *nd = nodes + cur;
-            const float4 *lo4 = reinterpret_cast<const float4 *>(nd->lo), *hi4 = reinterpret_cast<const float4 *>(nd->hi);
-            const float4 ax = __ldg(pos[0] ? lo4 + 0 : hi4 + 0), bx = __ldg(pos[0] ? hi4 + 0 : lo4 + 0);
-            const float4 ay = __ldg(pos[1] ? lo4 + 1 : hi4 + 1), by = __ldg(pos[1] ? hi4 + 1 : lo4 + 1);
-            const float4 az = __ldg(pos[2] ? lo4 + 2 : hi4 + 2), bz = __ldg(pos[2] ? hi4 + 2 : lo4 + 2);
-            const uint4 ch = __ldg(reinterpret_cast<const uint4 *>(nd->child));
+            float4 ax, bx, ay, by, az, bz;
+            uint4 ch;
+            if (TEXM != 0) {
+                const uint32_t tb = cur * 8u;   // eight uint4 texels per node; the plane arrays picked by index
+                const cudaTextureObject_t tx = (cudaTextureObject_t)sc.bvh_tex;
+                const uint4 *nq = reinterpret_cast<const uint4 *>(nd);
+#define BVH_F4(slot, i) (((TEXM >> (slot)) & 1) ? tex1Dfetch<uint4>(tx, (int)(tb + (i))) : __ldg(nq + (i)))
+                ax = u4f(BVH_F4(0, pos[0] ? 0u : 3u)); bx = u4f(BVH_F4(1, pos[0] ? 3u : 0u));
+                ay = u4f(BVH_F4(2, pos[1] ? 1u : 4u)); by = u4f(BVH_F4(3, pos[1] ? 4u : 1u));
+                az = u4f(BVH_F4(4, pos[2] ? 2u : 5u)); bz = u4f(BVH_F4(5, pos[2] ? 5u : 2u));
+                ch = BVH_F4(6, 6u);
+#undef BVH_F4
+            } else {
+                const float4 *lo4 = reinterpret_cast<const float4 *>(nd->lo), *hi4 = reinterpret_cast<const float4 *>(nd->hi);
+                ax = __ldg(pos[0] ? lo4 + 0 : hi4 + 0); bx = __ldg(pos[0] ? hi4 + 0 : lo4 + 0);
+                ay = __ldg(pos[1] ? lo4 + 1 : hi4 + 1); by = __ldg(pos[1] ? hi4 + 1 : lo4 + 1);
+                az = __ldg(pos[2] ? lo4 + 2 : hi4 + 2); bz = __ldg(pos[2] ? hi4 + 2 : lo4 + 2);
+                ch = __ldg(reinterpret_cast<const uint4 *>(nd->child));
+            }
             float key[4];
             uint32_t ref[4];
             ref[0] = ch.x; ref[1] = ch.y; ref[2] = ch.z; ref[3] = ch.w;
@@ -313,7 +350,7 @@ __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayC
     BvhTraversal<COUNT, SPH> T;
     T.begin(sc, r, cn);
     while (!T.done()) {
-        T.descend(sc, stack, stride, cn, BVH_DESCEND_MAX);
+        T.template descend<BVH_TEX_MASK>(sc, stack, stride, cn, BVH_DESCEND_MAX);
         if (T.done()) break;
         if (T.cur & BVH_LEAF) T.leaf(sc, stack, stride, cn);
     }

@@ -50,6 +50,7 @@ struct DevScene {
     const DevMaterial *materials;
     // BVH over sphere/triangle boxes (EXTENSION, flux_bvh.cuh; unused when the linear scan is selected)
     const void *bvh_nodes;      // BvhNode4[bvh_n_nodes]
+    unsigned long long bvh_tex; // the same nodes as a linear texture of uint4 texels (8 per node); 0 = none
     const uint32_t *bvh_prims;  // leaf primitive refs: (kind<<30 | index)
     const void *bvh_sph;        // SphRec[n_spheres]
     const void *bvh_tri;        // TriRec[n_tris]

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 1
 #endif
-template <bool COUNT>
+template <bool COUNT, int TEXM>
 __global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(const __grid_constant__ DevScene sc, uint64_t n,
                                                              unsigned long long *__restrict__ work,
                                                              const double *__restrict__ o, const double *__restrict__ d,
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(128, TRACE_MIN_BLOCKS) trace_rays_bvh_kernel(c
             continue;
         }
         if (has) {
-            T.descend(sc, stack, blockDim.x, cn, TRACE_DESCEND_MAX);
+            T.template descend<TEXM>(sc, stack, blockDim.x, cn, TRACE_DESCEND_MAX);
             if (!T.done() && (T.cur & BVH_LEAF)) T.leaf(sc, stack, blockDim.x, cn);
             if (T.done()) {
                 if (T.best.shape_id == 0xFFFFFFFFu) {
@@ -367,8 +367,12 @@ void launch_trace_rays(const DevScene &sc, uint64_t n, const double *o, const do
         const int blocks = (int)(want < cap ? want : cap);
         cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream);
         // with counters (flux_enable_counters): segments = rays, nodes_visited, bbox / triangle tests, candidates, misses
-        if (counters) trace_rays_bvh_kernel<true><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, counters);
-        else trace_rays_bvh_kernel<false><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, nullptr);
+        // node fetches split between the texture unit and the LSU (flux_bvh.cuh TRACE_TEX_MASK) when the nodes have a
+        // texture object; a tree too large for a linear texture goes through the LSU alone
+        if (counters) trace_rays_bvh_kernel<true, 0><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, counters);
+        else if (sc.bvh_tex != 0ull && TRACE_TEX_MASK != 0)
+            trace_rays_bvh_kernel<false, TRACE_TEX_MASK><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, nullptr);
+        else trace_rays_bvh_kernel<false, 0><<<blocks, threads, smem, stream>>>(sc, n, work, o, d, hit, t, nullptr);
     } else {
         uint64_t cap = (uint64_t)sm_count * 16;
         int blocks = (int)(want < cap ? want : cap);
