@@ -425,7 +425,9 @@ def bench_c5(env: Env, n_total: int, chunk: int):
                         "alg_bytes_per_ray": bpr, "nodes_per_ray": cn["nodes_visited"] / seg,
                         "sphere_records_per_ray": cn["bbox_tests"] / seg, "quadratics_per_ray": cn["bbox_pass"] / seg,
                         "peak_source": src, "note": "per GPU; nodes x 128 + sphere records x 112 + 68 B ray/result; the tree (1.5 MB) "
-                        "lives in L2 — latency / divergence bound, see ncu", "ncu": _ncu_note("trace_rays_bvh")}}
+                        "lives in L1 / L2, so this is not HBM traffic: the kernel is bound by the L1 data pipes (one wavefront "
+                        "per lane for an incoherent 16-byte fetch; fetches split between the texture unit and the LSU), see ncu",
+                        "ncu": _ncu_note("trace_rays_bvh")}}
     if env.rank == 0 and env.world == 1:
         from oracle import oracle_py as O
         t0 = time.perf_counter()
