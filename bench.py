@@ -210,9 +210,14 @@ def _ncu_note(key: str):
 class Env:
     """What the config legs share: the context, the process group, timing helpers."""
 
-    def __init__(self, ctx, torch, dist, world, rank, dev, peak_ginstr):
+    def __init__(self, ctx, torch, dist, world, rank, dev, peak_ginstr, sm_mhz=None):
         self.ctx, self.torch, self.dist, self.world, self.rank, self.dev = ctx, torch, dist, world, rank, dev
         self.peak_ginstr = peak_ginstr
+        props = torch.cuda.get_device_properties(dev)
+        # L1 data-pipe peak: one wavefront per SM and cycle on each of the two paths (LSU, texture unit); the SM clock is
+        # the one sampled under load during the headline (rank 0), else the device's maximum
+        self.sm_count = props.multi_processor_count
+        self.sm_ghz = (sm_mhz or getattr(props, "clock_rate", 1965000) / 1e3) / 1e3
         self.stream = torch.cuda.current_stream().cuda_stream
 
     def barrier(self):
@@ -330,6 +335,13 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
                            "note": "per GPU; algorithmic bytes = nodes x 128 + sphere records x 112 + triangle records x 96 (SURVEY.md "
                                    "§8d); served mostly from L2 — the kernel is latency / divergence bound, see ncu",
                            "ncu": _ncu_note("render_regen_bvh")}
+        # the same work as 16-byte fetches against the LSU data pipe (one wavefront per lane and fetch; the render kernels
+        # do not use the texture path): 7 per node, 7 per sphere record, 6 per triangle record
+        fps = (tot["nodes_visited"] * 7 + tot["bbox_tests"] * 7 + tot["tri_tests"] * 6) / seg
+        l1_peak = env.sm_count * env.sm_ghz
+        l1_ach = fps * tot["segments"] * scale / (kernel_ms * 1e-3) / 1e9 / env.world
+        out["roofline"]["l1_lsu_data_pipe"] = {"achieved": l1_ach, "peak": l1_peak, "unit": "Gwavefronts/s", "frac": l1_ach / l1_peak,
+                                               "fetches_per_segment": fps}
     if env.rank == 0 and env.world == 1 and cpu_fn is not None:
         out["cpu_baseline"] = cpu_fn()
     return out
@@ -415,18 +427,27 @@ def bench_c5(env: Env, n_total: int, chunk: int):
     hbm, src = _hbm_peak()
     rays = chunk * n_chunks
     gbs = bpr * (rays / env.world) / (k_max * 1e-3) / 1e9
+    # what bounds the kernel: the L1 data pipes.  An incoherent 16-byte fetch costs a pipe one wavefront
+    # per lane; a node is 7 such fetches, a sphere record 7, the ray 3 and its result 1
+    fpr = (cn["nodes_visited"] * 7 + cn["bbox_tests"] * 7) / seg + 4
+    l1_peak = env.sm_count * env.sm_ghz * 2.0            # G wavefronts/s: LSU + texture unit
+    l1_ach = fpr * (rays / env.world) / (k_max * 1e-3) / 1e9
     out = {"workload": f"{rays} random rays x 10000 spheres (BVH), ids and t per ray", "n_gpus": env.world,
            "value": rays / e2e_max / 1e6, "unit": "Mrays/s",
            "value_region": "flux_trace_rays with pinned host buffers: ray H2D + kernel + result D2H, pipelined in 4 Mi-ray pieces over three streams",
            "value_resident": rays / (k_max * 1e-3) / 1e6, "kernel_ms": k_max,
            "h2d_bytes_per_step": rays * 48, "d2h_bytes_per_step": rays * 12,
            "hit_fraction": hits_all / rays, "hit_id_checksum_rank0": csum,
-           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
-                        "alg_bytes_per_ray": bpr, "nodes_per_ray": cn["nodes_visited"] / seg,
+           "roofline": {"bound": "l1_data_pipes", "achieved": l1_ach, "peak": l1_peak, "unit": "Gwavefronts/s", "frac": l1_ach / l1_peak,
+                        "traffic": None, "fetches_per_ray": fpr, "nodes_per_ray": cn["nodes_visited"] / seg,
                         "sphere_records_per_ray": cn["bbox_tests"] / seg, "quadratics_per_ray": cn["bbox_pass"] / seg,
-                        "peak_source": src, "note": "per GPU; nodes x 128 + sphere records x 112 + 68 B ray/result; the tree (1.5 MB) "
-                        "lives in L1 / L2, so this is not HBM traffic: the kernel is bound by the L1 data pipes (one wavefront "
-                        "per lane for an incoherent 16-byte fetch; fetches split between the texture unit and the LSU), see ncu",
+                        "peak_source": f"{env.sm_count} SMs x {env.sm_ghz:.3f} GHz x 2 data paths (LSU + texture unit), one wavefront "
+                                       "per path and cycle (ncu l1tex__data_pipe_*_wavefronts peak)",
+                        "note": "per GPU; algorithmic 16-byte fetches per ray (7 per node, 7 per sphere record, 3 + 1 for the ray and "
+                                "its result) / kernel time; the tree (1.5 MB) lives in L1 / L2, so HBM is not the bound — "
+                                "hbm_equivalent is the same work in bytes against the HBM figure, for SURVEY.md §8d's per-unit bytes",
+                        "hbm_equivalent": {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "alg_bytes_per_ray": bpr,
+                                           "peak_source": src},
                         "ncu": _ncu_note("trace_rays_bvh")}}
     if env.rank == 0 and env.world == 1:
         from oracle import oracle_py as O
@@ -648,7 +669,7 @@ def main():
     which = set() if args.configs in ("none", "") else set(args.configs.split(","))
     configs = None
     if which:
-        env = Env(ctx, torch, dist, world, rank, dev, peak_ginstr)
+        env = Env(ctx, torch, dist, world, rank, dev, peak_ginstr, (clk or {}).get("sm_mhz"))
         ctx.set_kernel_mode(0)
         t0 = time.perf_counter()
         configs = run_configs(env, which)
