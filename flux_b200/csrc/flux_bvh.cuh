@@ -104,7 +104,8 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 // (mask 0, the r1 code): config 3 with any mask 862 - 890 against 934 Msamples/s — their L1 hit rate is 51 %, an L1 hit
 // is quick through the LSU and as slow as a miss through the texture pipe, and they are issue-bound as much as L1-bound
 // (the children fetch alone through the texture unit: 871; the plane arrays picked by a 32-bit index instead of by
-// pointer, all on the LSU: 869 — the compiler keeps six offsets live per ray and the kernel spills).  Pairs of predicated
+// pointer, all on the LSU: 869 — the compiler keeps six offsets live per ray and the kernel spills; the triangle records
+// of the leaves through a texture of their own, all four 16-byte pieces or two of them: 879 / 882 / 870).  Pairs of predicated
 // loads at immediate offsets (`@p ld [node+lo]; @!p ld [node+hi]`, no address arithmetic at all): config 5 3269 against
 // 3462, config 3 630 against 934 — a load whose predicate is off is not free.
 #ifndef TRACE_TEX_MASK
