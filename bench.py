@@ -335,13 +335,6 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
                            "note": "per GPU; algorithmic bytes = nodes x 128 + sphere records x 112 + triangle records x 96 (SURVEY.md "
                                    "§8d); served mostly from L2 — the kernel is latency / divergence bound, see ncu",
                            "ncu": _ncu_note("render_regen_bvh")}
-        # the same work as 16-byte fetches against the LSU data pipe (one wavefront per lane and fetch; the render kernels
-        # do not use the texture path): 7 per node, 7 per sphere record, 6 per triangle record
-        fps = (tot["nodes_visited"] * 7 + tot["bbox_tests"] * 7 + tot["tri_tests"] * 6) / seg
-        l1_peak = env.sm_count * env.sm_ghz
-        l1_ach = fps * tot["segments"] * scale / (kernel_ms * 1e-3) / 1e9 / env.world
-        out["roofline"]["l1_lsu_data_pipe"] = {"achieved": l1_ach, "peak": l1_peak, "unit": "Gwavefronts/s", "frac": l1_ach / l1_peak,
-                                               "fetches_per_segment": fps}
     if env.rank == 0 and env.world == 1 and cpu_fn is not None:
         out["cpu_baseline"] = cpu_fn()
     return out
