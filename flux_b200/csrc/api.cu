@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -427,7 +428,10 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
             cudaDestroyTextureObject(ctx->bvh_tex);
             ctx->bvh_tex = 0;
         }
-        {   // the nodes once more as a linear texture: eight uint4 texels per node
+        // the nodes once more as a linear texture, eight uint4 texels per node (flux_bvh.cuh TRACE_TEX_MASK).  A tree too
+        // large for a linear texture — or FLUXB200_NO_NODE_TEXTURE in the environment, a test hook — leaves bvh_tex 0 and
+        // the ray-batch kernel on its LSU-only instantiation
+        if (!std::getenv("FLUXB200_NO_NODE_TEXTURE")) {
             cudaResourceDesc rd{};
             rd.resType = cudaResourceTypeLinear;
             rd.res.linear.devPtr = ctx->bvh_nodes.p;

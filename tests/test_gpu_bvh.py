@@ -39,6 +39,20 @@ def test_bvh_matches_linear_scan_10k_spheres_4m_rays(gpu_ctx):
     assert 0.02 < (bvh[0] >= 0).mean() < 0.98
 
 
+def test_ray_batch_kernel_without_node_texture_is_bitwise_the_same(gpu_ctx, monkeypatch):
+    """The ray-batch kernel fetches four of a node's seven 16-byte pieces through the texture unit (flux_bvh.cuh
+    TRACE_TEX_MASK); a tree that cannot be bound as a linear texture runs the LSU-only instantiation.  Both return the
+    same ids and the same bits of t."""
+    flat = synth.sphere_cloud_scene(10_000, seed=7).flatten()
+    o, d = synth.random_rays(1_000_000, seed=7)
+    with_tex = _trace(gpu_ctx, flat, o, d, 2)
+    monkeypatch.setenv("FLUXB200_NO_NODE_TEXTURE", "1")
+    without = _trace(gpu_ctx, flat, o, d, 2)
+    monkeypatch.delenv("FLUXB200_NO_NODE_TEXTURE")
+    _same(with_tex, without)
+    assert 0.02 < (with_tex[0] >= 0).mean() < 0.98
+
+
 def test_bvh_ieee_corner_rays(gpu_ctx):
     """Axis-parallel rays (1/0 = inf and 0*inf = NaN slabs), rays starting inside spheres, on box faces, zero and
     denormal directions, unnormalised directions: NaN slabs must never cull."""
