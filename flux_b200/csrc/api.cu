@@ -8,8 +8,10 @@
 #include "../../include/fluxb200.h"
 #include "flux_bvh.cuh"
 #include "flux_kernels.cuh"
+#include "host_slices.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -175,18 +177,20 @@ void flatten_spheres(const flux_scene_flat *s, std::vector<double> &sph, std::ve
 // triangles (EXTENSION) as SoA: v0, e1 = v1 - v0, e2 = v2 - v0
 void flatten_triangles(const flux_scene_flat *s, std::vector<double> &tri, std::vector<uint32_t> &tri_meta) {
     const uint32_t nt = s->n_triangles;
-    tri.assign((size_t)TRI_FIELDS * nt, 0.0);
-    tri_meta.assign((size_t)2 * nt, 0u);
-    for (uint32_t i = 0; i < nt; i++) {
-        for (int k = 0; k < 3; k++) {
-            const double v0 = s->tri_v0[3 * (size_t)i + k];
-            tri[(size_t)(TRI_V0X + k) * nt + i] = v0;
-            tri[(size_t)(TRI_E1X + k) * nt + i] = s->tri_v1[3 * (size_t)i + k] - v0;
-            tri[(size_t)(TRI_E2X + k) * nt + i] = s->tri_v2[3 * (size_t)i + k] - v0;
+    tri.resize((size_t)TRI_FIELDS * nt);
+    tri_meta.resize((size_t)2 * nt);
+    flux_in_slices(nt, [&](uint32_t lo, uint32_t hi) {   // a million triangles: on several host threads
+        for (uint32_t i = lo; i < hi; i++) {
+            for (int k = 0; k < 3; k++) {
+                const double v0 = s->tri_v0[3 * (size_t)i + k];
+                tri[(size_t)(TRI_V0X + k) * nt + i] = v0;
+                tri[(size_t)(TRI_E1X + k) * nt + i] = s->tri_v1[3 * (size_t)i + k] - v0;
+                tri[(size_t)(TRI_E2X + k) * nt + i] = s->tri_v2[3 * (size_t)i + k] - v0;
+            }
+            tri_meta[i] = s->tri_shape_id[i];
+            tri_meta[nt + i] = s->tri_material[i];
         }
-        tri_meta[i] = s->tri_shape_id[i];
-        tri_meta[nt + i] = s->tri_material[i];
-    }
+    });
 }
 
 V3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
@@ -293,11 +297,24 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     // Triangles are this library's extension and their vertices must be finite — whichever way the closest hit is then
     // found, so that adding an unrelated shape (and with it the BVH, whose builder has no box for such a triangle)
     // never turns a scene that rendered into an error.  Spheres and planes keep the reference's semantics: anything goes.
-    for (uint32_t i = 0; i < s->n_triangles; i++)
-        for (int k = 0; k < 3; k++)
-            if (!std::isfinite(s->tri_v0[3 * (size_t)i + k]) || !std::isfinite(s->tri_v1[3 * (size_t)i + k]) ||
-                !std::isfinite(s->tri_v2[3 * (size_t)i + k]))
-                return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: triangle " + std::to_string(i) + " has a non-finite vertex");
+    {
+        std::atomic<uint32_t> first_bad{0xFFFFFFFFu};   // the lowest index, whichever host thread meets it
+        flux_in_slices(s->n_triangles, [&](uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; i++) {
+                bool finite = true;
+                for (int k = 0; k < 3; k++)
+                    finite = finite && std::isfinite(s->tri_v0[3 * (size_t)i + k]) && std::isfinite(s->tri_v1[3 * (size_t)i + k]) &&
+                             std::isfinite(s->tri_v2[3 * (size_t)i + k]);
+                if (!finite) {
+                    uint32_t seen = first_bad.load();
+                    while (i < seen && !first_bad.compare_exchange_weak(seen, i)) {}
+                    return;   // later triangles of this slice have higher indices
+                }
+            }
+        });
+        if (first_bad.load() != 0xFFFFFFFFu)
+            return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: triangle " + std::to_string(first_bad.load()) + " has a non-finite vertex");
+    }
 
     DeviceGuard g(ctx->device);
     ctx->have_scene = false;

