@@ -44,7 +44,7 @@ struct Item {
 };
 
 struct Builder {
-    std::vector<Item> items;
+    flux_raw_vector<Item> items;
     BvhBuild *out;
     uint32_t leaf_size;
     double pad;
@@ -265,20 +265,6 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     out.tri.resize(nt);
     // independent per triangle: in slices on several host threads when there are many (host_slices.h)
     const auto in_slices = flux_in_slices;
-    // union over the items of a box each of them gives (min / max are exact: the order of the union does not matter)
-    auto union_of = [in_slices](const std::vector<Item> &items, const std::function<Box(const Item &)> &of) {
-        std::mutex mu;
-        Box total;
-        total.reset();
-        in_slices((uint32_t)items.size(), [&](uint32_t lo_i, uint32_t hi_i) {
-            Box part;
-            part.reset();
-            for (uint32_t i = lo_i; i < hi_i; i++) part.grow(of(items[i]));
-            std::lock_guard<std::mutex> g(mu);
-            total.grow(part);
-        });
-        return total;
-    };
     in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
     for (uint32_t i = lo_i; i < hi_i; i++) {
         TriRec &q = out.tri[i];
@@ -299,6 +285,11 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return false;
         return true;
     };
+    // The bounds the later steps need — of the centroids (what "large" is measured against) and of the boxes (the padding
+    // scale) — are gathered in the passes that make the items, per slice; min / max are exact, so the order of the unions
+    // does not matter.
+    Box sph_cb, tri_cb, tri_all;
+    sph_cb.reset(); tri_cb.reset(); tri_all.reset();
     for (uint32_t i = 0; i < ns; i++) {
         Item it;
         const SphRec &s = out.sph[i];
@@ -310,7 +301,11 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             out.linear.push_back(i);
             continue;
         }
-        for (int k = 0; k < 3; k++) it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+        for (int k = 0; k < 3; k++) {
+            it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+            sph_cb.lo[k] = std::min(sph_cb.lo[k], it.c[k]);
+            sph_cb.hi[k] = std::max(sph_cb.hi[k], it.c[k]);
+        }
         B.items.push_back(it);
     }
     const size_t tri_base = B.items.size();
@@ -318,6 +313,8 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     std::vector<uint32_t> first_bad(1, 0xFFFFFFFFu);
     std::mutex bad_mu;
     in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
+    Box part_c, part_b;
+    part_c.reset(); part_b.reset();
     for (uint32_t i = lo_i; i < hi_i; i++) {
         Item it;
         const TriRec &q = out.tri[i];
@@ -338,8 +335,16 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             std::lock_guard<std::mutex> g(bad_mu);
             first_bad[0] = std::min(first_bad[0], i);   // the lowest index, whichever thread saw it
         }
+        part_b.grow(it.box);
+        for (int k = 0; k < 3; k++) {
+            part_c.lo[k] = std::min(part_c.lo[k], it.c[k]);
+            part_c.hi[k] = std::max(part_c.hi[k], it.c[k]);
+        }
         B.items[tri_base + i] = it;
     }
+    std::lock_guard<std::mutex> g(bad_mu);
+    tri_cb.grow(part_c);
+    tri_all.grow(part_b);
     });
     if (first_bad[0] != 0xFFFFFFFFu) {
         err = "bvh: triangle " + std::to_string(first_bad[0]) + " has a non-finite vertex";
@@ -355,11 +360,8 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
             return std::sqrt(x * x + y * y + z * z);
         };
         // centroid bounds of everything approximate the populated region
-        const Box cb = union_of(B.items, [](const Item &it) {
-            Box p;
-            for (int k = 0; k < 3; k++) p.lo[k] = p.hi[k] = it.c[k];
-            return p;
-        });
+        Box cb = sph_cb;
+        cb.grow(tri_cb);
         std::vector<std::pair<double, size_t>> big;
         for (size_t k = 0; k < tri_base; k++) big.push_back({diag_of(B.items[k].box), k});   // the spheres stand first
         std::sort(big.begin(), big.end(), [](auto &p, auto &q) { return p.first > q.first || (p.first == q.first && p.second < q.second); });
@@ -396,7 +398,18 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     std::sort(out.linear.begin(), out.linear.end());
     if (B.items.empty()) return true;  // tree-less: linear list only
 
-    const Box all = union_of(B.items, [](const Item &it) { return it.box; });
+    Box all = tri_all;   // ... and the spheres that stayed (they stand first, in their order)
+    {
+        const size_t n_sph_items = B.items.size() - nt;
+        std::mutex mu;
+        in_slices((uint32_t)n_sph_items, [&](uint32_t lo_i, uint32_t hi_i) {
+            Box part;
+            part.reset();
+            for (uint32_t i = lo_i; i < hi_i; i++) part.grow(B.items[i].box);
+            std::lock_guard<std::mutex> g(mu);
+            all.grow(part);
+        });
+    }
     double ext = 0.0;
     for (int k = 0; k < 3; k++) ext = std::max({ext, std::fabs(all.lo[k]), std::fabs(all.hi[k])});
     out.extent = ext;
@@ -441,7 +454,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         out.nodes.clear();
         out.prims.clear();
         out.depth = 0;
-        out.prims.assign(n, 0u);
+        out.prims.resize(n);   // every entry is written by the leaf that covers it (make_leaf)
         if (n <= leaf) {  // a single leaf under a root node
             out.nodes.resize(1);
             BvhNode4 &r = out.nodes[0];

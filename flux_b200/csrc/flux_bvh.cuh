@@ -366,12 +366,13 @@ __device__ __forceinline__ HitRef closest_hit_bvh(const DevScene &sc, const RayC
 // ---- host builder (bvh_build.cu) ----
 #include <string>
 #include <vector>
+#include "host_slices.h"
 struct BvhBuild {
-    std::vector<BvhNode4> nodes;
-    std::vector<uint32_t> prims;     // (kind << 30) | index, in leaf order
+    flux_raw_vector<BvhNode4> nodes;   // (resize() does not zero these three: host_slices.h)
+    flux_raw_vector<uint32_t> prims;   // (kind << 30) | index, in leaf order
     std::vector<uint32_t> linear;    // sphere indices kept out of the tree
     std::vector<SphRec> sph;         // [n_spheres], indexed like the SoA arrays
-    std::vector<TriRec> tri;         // [n_triangles]
+    flux_raw_vector<TriRec> tri;     // [n_triangles]
     double extent = 0.0;             // max |coordinate| over the boxes in the tree
     uint32_t depth = 0;              // levels of 4-wide nodes
     uint32_t leaf_size = 0;

@@ -7,9 +7,24 @@
 #include <algorithm>
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <system_error>
 #include <thread>
+#include <utility>
 #include <vector>
+
+// A vector whose resize() leaves trivially constructible elements unwritten: the hundred-megabyte arrays of a
+// million-triangle scene are then first touched (and their pages faulted in) by the slices that fill them, on several
+// threads, instead of being zeroed by one.  Every element is written before it is read — the arrays that go to the
+// device are hashed whole by flux_bvh_hash, so a byte left behind would show as a tree that differs from run to run.
+template <class T> struct flux_noinit_alloc : std::allocator<T> {
+    template <class U> struct rebind { using other = flux_noinit_alloc<U>; };
+    flux_noinit_alloc() = default;
+    template <class U> flux_noinit_alloc(const flux_noinit_alloc<U> &) {}
+    template <class U> void construct(U *p) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using flux_raw_vector = std::vector<T, flux_noinit_alloc<T>>;
 
 template <class F> inline void flux_spawn_or_run(std::vector<std::thread> &pool, F f) {
     try {
