@@ -175,9 +175,9 @@ void flatten_spheres(const flux_scene_flat *s, std::vector<double> &sph, std::ve
 }
 
 // triangles (EXTENSION) as SoA: v0, e1 = v1 - v0, e2 = v2 - v0
-void flatten_triangles(const flux_scene_flat *s, std::vector<double> &tri, std::vector<uint32_t> &tri_meta) {
+void flatten_triangles(const flux_scene_flat *s, flux_raw_vector<double> &tri, flux_raw_vector<uint32_t> &tri_meta) {
     const uint32_t nt = s->n_triangles;
-    tri.resize((size_t)TRI_FIELDS * nt);
+    tri.resize((size_t)TRI_FIELDS * nt);   // not zeroed (host_slices.h): every element is written below
     tri_meta.resize((size_t)2 * nt);
     flux_in_slices(nt, [&](uint32_t lo, uint32_t hi) {   // a million triangles: on several host threads
         for (uint32_t i = lo; i < hi; i++) {
@@ -364,8 +364,8 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
         pln_meta[i] = s->plane_shape_id[i];
         pln_meta[np + i] = s->plane_material[i];
     }
-    std::vector<double> tri;
-    std::vector<uint32_t> tri_meta;
+    flux_raw_vector<double> tri;
+    flux_raw_vector<uint32_t> tri_meta;
     flatten_triangles(s, tri, tri_meta);
     CK(ctx->materials.reserve(mats.size()));
     CK(ctx->sph.reserve(sph.size()));
@@ -1127,8 +1127,10 @@ int flux_bvh_hash(const flux_scene_flat *s, uint64_t *hash) {
     if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
         (nt && (!s->tri_v0 || !s->tri_v1 || !s->tri_v2 || !s->tri_shape_id || !s->tri_material)))
         return FLUX_ERR_INVALID;
-    std::vector<double> sph, tri;
-    std::vector<uint32_t> sph_meta, tri_meta;
+    std::vector<double> sph;
+    std::vector<uint32_t> sph_meta;
+    flux_raw_vector<double> tri;
+    flux_raw_vector<uint32_t> tri_meta;
     flatten_spheres(s, sph, sph_meta);
     flatten_triangles(s, tri, tri_meta);
     BvhBuild bb;
@@ -1160,8 +1162,10 @@ int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
     if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
         (nt && (!s->tri_v0 || !s->tri_v1 || !s->tri_v2 || !s->tri_shape_id || !s->tri_material)))
         return FLUX_ERR_INVALID;
-    std::vector<double> sph, tri;
-    std::vector<uint32_t> sph_meta, tri_meta;
+    std::vector<double> sph;
+    std::vector<uint32_t> sph_meta;
+    flux_raw_vector<double> tri;
+    flux_raw_vector<uint32_t> tri_meta;
     flatten_spheres(s, sph, sph_meta);
     flatten_triangles(s, tri, tri_meta);
     BvhBuild bb;

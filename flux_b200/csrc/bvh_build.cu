@@ -37,14 +37,18 @@ struct Box {
     }
 };
 
+// What the median splits move about is 32 bytes per primitive — the split key and where the box is — not the 80 of key
+// and box together: the selection passes are bound by memory traffic, and a box is looked at once, when its leaf is made.
 struct Item {
-    Box box;
     double c[3];      // centroid (split key only)
     uint32_t ref;     // (kind << 30) | index
+    uint32_t slot;    // its box: Builder::boxes[slot]
 };
+static_assert(sizeof(Item) == 32, "Item layout");
 
 struct Builder {
-    flux_raw_vector<Item> items;
+    Item *items = nullptr;        // the primitives in the tree, a view into the caller's storage
+    const Box *boxes = nullptr;   // by Item::slot
     BvhBuild *out;
     uint32_t leaf_size;
     double pad;
@@ -52,7 +56,7 @@ struct Builder {
     Box bounds(uint32_t a, uint32_t b) const {
         Box x;
         x.reset();
-        for (uint32_t i = a; i < b; i++) x.grow(items[i].box);
+        for (uint32_t i = a; i < b; i++) x.grow(boxes[items[i].slot]);
         return x;
     }
     bool presplit = false;   // partition() has already put every range in its final order: split() only names the middle
@@ -103,7 +107,7 @@ struct Builder {
         for (int k = 1; k < 3; k++)
             if (hi[k] - lo[k] > hi[ax] - lo[ax]) ax = k;
         const uint32_t mid = a + (b - a + 1) / 2;
-        std::nth_element(items.begin() + a, items.begin() + mid, items.begin() + b, [ax](const Item &p, const Item &q) {
+        std::nth_element(items + a, items + mid, items + b, [ax](const Item &p, const Item &q) {
             return p.c[ax] < q.c[ax] || (p.c[ax] == q.c[ax] && p.ref < q.ref);
         });
         return mid;
@@ -279,7 +283,8 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     // ---- primitive boxes ----
     Builder B;
     B.out = &out;
-    B.items.reserve((size_t)ns + nt);
+    flux_raw_vector<Item> items((size_t)ns + nt);   // spheres first (those with a finite box), then the triangles
+    flux_raw_vector<Box> boxes((size_t)ns + nt);    // boxes[k] belongs to the item made k-th, wherever the splits move it
     auto finite_box = [](const Box &b) {
         for (int k = 0; k < 3; k++)
             if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return false;
@@ -290,26 +295,29 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     // does not matter.
     Box sph_cb, tri_cb, tri_all;
     sph_cb.reset(); tri_cb.reset(); tri_all.reset();
+    size_t tri_base = 0;
     for (uint32_t i = 0; i < ns; i++) {
         Item it;
+        Box bx;
         const SphRec &s = out.sph[i];
-        it.box.lo[0] = std::min(s.c0x, s.c1x); it.box.hi[0] = std::max(s.c0x, s.c1x);   // negative radii swap corners
-        it.box.lo[1] = std::min(s.c0y, s.c1y); it.box.hi[1] = std::max(s.c0y, s.c1y);
-        it.box.lo[2] = std::min(s.c0z, s.c1z); it.box.hi[2] = std::max(s.c0z, s.c1z);
+        bx.lo[0] = std::min(s.c0x, s.c1x); bx.hi[0] = std::max(s.c0x, s.c1x);   // negative radii swap corners
+        bx.lo[1] = std::min(s.c0y, s.c1y); bx.hi[1] = std::max(s.c0y, s.c1y);
+        bx.lo[2] = std::min(s.c0z, s.c1z); bx.hi[2] = std::max(s.c0z, s.c1z);
         it.ref = ((uint32_t)KIND_SPHERE << 30) | i;
-        if (!finite_box(it.box)) {  // NaN / inf geometry: keep the linear scan's verdict by testing it linearly
+        if (!finite_box(bx)) {  // NaN / inf geometry: keep the linear scan's verdict by testing it linearly
             out.linear.push_back(i);
             continue;
         }
         for (int k = 0; k < 3; k++) {
-            it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+            it.c[k] = 0.5 * bx.lo[k] + 0.5 * bx.hi[k];
             sph_cb.lo[k] = std::min(sph_cb.lo[k], it.c[k]);
             sph_cb.hi[k] = std::max(sph_cb.hi[k], it.c[k]);
         }
-        B.items.push_back(it);
+        it.slot = (uint32_t)tri_base;
+        boxes[tri_base] = bx;
+        items[tri_base++] = it;
     }
-    const size_t tri_base = B.items.size();
-    B.items.resize(tri_base + nt);
+    const size_t n_items = tri_base + nt;
     std::vector<uint32_t> first_bad(1, 0xFFFFFFFFu);
     std::mutex bad_mu;
     in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
@@ -317,30 +325,33 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     part_c.reset(); part_b.reset();
     for (uint32_t i = lo_i; i < hi_i; i++) {
         Item it;
+        Box bx;
         const TriRec &q = out.tri[i];
         const double v0[3] = {q.v0x, q.v0y, q.v0z};
         for (int k = 0; k < 3; k++) {
             const double a = v0[k], b = tri_v1[3 * (size_t)i + k], c = tri_v2[3 * (size_t)i + k];
             // the device works with e1 = v1 - v0, e2 = v2 - v0: cover both the given and the reconstructed vertices
             const double e1 = (k == 0 ? q.e1x : k == 1 ? q.e1y : q.e1z), e2 = (k == 0 ? q.e2x : k == 1 ? q.e2y : q.e2z);
-            it.box.lo[k] = std::min({a, b, c, a + e1, a + e2});
-            it.box.hi[k] = std::max({a, b, c, a + e1, a + e2});
-            it.c[k] = 0.5 * it.box.lo[k] + 0.5 * it.box.hi[k];
+            bx.lo[k] = std::min({a, b, c, a + e1, a + e2});
+            bx.hi[k] = std::max({a, b, c, a + e1, a + e2});
+            it.c[k] = 0.5 * bx.lo[k] + 0.5 * bx.hi[k];
         }
         it.ref = ((uint32_t)KIND_TRI << 30) | i;
-        bool finite = finite_box(it.box);
+        it.slot = (uint32_t)(tri_base + i);
+        bool finite = finite_box(bx);
         for (int k = 0; k < 3; k++)   // min / max skip a NaN or not depending on where it stands: look at the vertices themselves
             finite = finite && std::isfinite(v0[k]) && std::isfinite(tri_v1[3 * (size_t)i + k]) && std::isfinite(tri_v2[3 * (size_t)i + k]);
         if (!finite) {
             std::lock_guard<std::mutex> g(bad_mu);
             first_bad[0] = std::min(first_bad[0], i);   // the lowest index, whichever thread saw it
         }
-        part_b.grow(it.box);
+        part_b.grow(bx);
         for (int k = 0; k < 3; k++) {
             part_c.lo[k] = std::min(part_c.lo[k], it.c[k]);
             part_c.hi[k] = std::max(part_c.hi[k], it.c[k]);
         }
-        B.items[tri_base + i] = it;
+        boxes[tri_base + i] = bx;
+        items[tri_base + i] = it;
     }
     std::lock_guard<std::mutex> g(bad_mu);
     tri_cb.grow(part_c);
@@ -352,8 +363,9 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     }
     lap("boxes");
     // ---- oversized spheres go to the linear list (at most 64, largest first) ----
-    // Only spheres are ever moved, so a set of items without one (and the common case of a handful of spheres beside a
-    // mesh, where none turns out oversized) costs no pass over — and no copy of — the million triangles beside them.
+    // Only spheres are ever moved, and they stand first: the ones that stay close up towards the triangles and the tree's
+    // items begin that many places later — no pass over, and no copy of, the million triangles behind them.
+    size_t first_item = 0;
     if (tri_base > 0) {
         auto diag_of = [](const Box &b) {
             const double x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
@@ -363,49 +375,60 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         Box cb = sph_cb;
         cb.grow(tri_cb);
         std::vector<std::pair<double, size_t>> big;
-        for (size_t k = 0; k < tri_base; k++) big.push_back({diag_of(B.items[k].box), k});   // the spheres stand first
+        for (size_t k = 0; k < tri_base; k++) big.push_back({diag_of(boxes[k]), k});
         std::sort(big.begin(), big.end(), [](auto &p, auto &q) { return p.first > q.first || (p.first == q.first && p.second < q.second); });
         if (big.size() > 64) big.resize(64);
         std::vector<size_t> drop;
         const double scene = diag_of(cb);
-        bool any_large = false;
-        for (auto &p : big) any_large = any_large || p.first > 0.25 * scene;
-        if (B.items.size() > 64 && any_large) {
-            // median-based scale so that one environment sphere does not define "large"
-            std::vector<double> all_diag(B.items.size());
-            in_slices((uint32_t)B.items.size(), [&](uint32_t lo_i, uint32_t hi_i) {
-                for (uint32_t i = lo_i; i < hi_i; i++) all_diag[i] = diag_of(B.items[i].box);
+        std::vector<std::pair<double, size_t>> large;   // the candidates: large against the populated region ...
+        for (auto &p : big)
+            if (p.first > 0.25 * scene) large.push_back(p);
+        if (n_items > 64 && !large.empty()) {
+            // ... and against 16 times the median diagonal, so that one environment sphere does not define "large".  The
+            // median itself is not needed: x -> 16.0 * x is monotone, so 16 * median < d exactly when more than half of the
+            // diagonals (n / 2 + 1 of them: the median is the element of rank n / 2) have 16 * diagonal < d — one counting
+            // pass in slices, no array of a million diagonals to select in.
+            std::vector<uint64_t> below(large.size(), 0);
+            std::mutex mu;
+            in_slices((uint32_t)n_items, [&](uint32_t lo_i, uint32_t hi_i) {
+                std::vector<uint64_t> mine(large.size(), 0);
+                for (uint32_t i = lo_i; i < hi_i; i++) {
+                    const double d16 = 16.0 * diag_of(boxes[i]);
+                    for (size_t c = 0; c < large.size(); c++) mine[c] += d16 < large[c].first;
+                }
+                std::lock_guard<std::mutex> g(mu);
+                for (size_t c = 0; c < large.size(); c++) below[c] += mine[c];
             });
-            std::nth_element(all_diag.begin(), all_diag.begin() + all_diag.size() / 2, all_diag.end());
-            const double median = all_diag[all_diag.size() / 2];
-            for (auto &p : big)
-                if (p.first > 0.25 * scene && p.first > 16.0 * median) drop.push_back(p.second);
+            for (size_t c = 0; c < large.size(); c++)
+                if (below[c] >= (uint64_t)n_items / 2 + 1) drop.push_back(large[c].second);
         }
-        if (!drop.empty()) {   // at most 64, all among the leading spheres: close the gaps in place, order kept
+        if (!drop.empty()) {   // at most 64, all among the leading spheres; the order of the others is kept
             std::sort(drop.begin(), drop.end());
-            for (size_t k : drop) out.linear.push_back(B.items[k].ref & 0x3FFFFFFFu);
-            size_t w = drop[0], d = 0;
-            for (size_t k = drop[0]; k < B.items.size(); k++) {
-                if (d < drop.size() && drop[d] == k) {
-                    d++;
+            for (size_t k : drop) out.linear.push_back(items[k].ref & 0x3FFFFFFFu);
+            size_t w = tri_base, d = drop.size();
+            for (size_t k = tri_base; k-- > 0;) {
+                if (d > 0 && drop[d - 1] == k) {
+                    d--;
                     continue;
                 }
-                B.items[w++] = B.items[k];
+                items[--w] = items[k];
             }
-            B.items.resize(w);
+            first_item = w;   // == drop.size()
         }
     }
     std::sort(out.linear.begin(), out.linear.end());
-    if (B.items.empty()) return true;  // tree-less: linear list only
+    const uint64_t n = n_items - first_item;
+    if (n == 0) return true;  // tree-less: linear list only
+    B.items = items.data() + first_item;
+    B.boxes = boxes.data();
 
-    Box all = tri_all;   // ... and the spheres that stayed (they stand first, in their order)
+    Box all = tri_all;   // ... and the spheres that stayed
     {
-        const size_t n_sph_items = B.items.size() - nt;
         std::mutex mu;
-        in_slices((uint32_t)n_sph_items, [&](uint32_t lo_i, uint32_t hi_i) {
+        in_slices((uint32_t)(tri_base - first_item), [&](uint32_t lo_i, uint32_t hi_i) {
             Box part;
             part.reset();
-            for (uint32_t i = lo_i; i < hi_i; i++) part.grow(B.items[i].box);
+            for (uint32_t i = lo_i; i < hi_i; i++) part.grow(boxes[B.items[i].slot]);
             std::lock_guard<std::mutex> g(mu);
             all.grow(part);
         });
@@ -417,7 +440,6 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
 
     lap("oversized");
     // ---- leaf size: smallest in {4, 8} whose (balanced) tree fits the traversal stack ----
-    const uint64_t n = B.items.size();
     // where a range is cut depends on its length only, so the depth of the tree for a given leaf size is known
     // before anything is moved: levels(m) = 1 + the deepest of the four quarters that are still larger than a leaf
     auto levels_for = [](uint64_t total, uint32_t leaf) {

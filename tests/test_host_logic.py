@@ -191,6 +191,27 @@ def test_bvh_builder_is_deterministic_and_plans_its_depth():
     assert (levels, leaf, prims, violations, miscounted) == (10, 4, n, 0, 0)
 
 
+def test_bvh_builder_writes_every_byte_it_hands_over():
+    """The builder's large arrays are not zeroed before the slices fill them (flux_raw_vector, host_slices.h).  glibc's
+    MALLOC_PERTURB_ fills every allocation with a byte pattern instead of leaving the fresh zero pages of a large
+    mmap: a byte of the node, reference or record arrays that no slice wrote would change the hash."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C\nfrom flux_b200 import _capi, synth\n"
+            "for sd in (synth.mesh_scene(300, 200, seed=3), synth.sphere_cloud_scene(20_000, seed=6)):\n"
+            "    out = C.c_uint64(); flat = sd.flatten()\n"
+            "    assert _capi.lib().flux_bvh_hash(flat.ptr(), C.byref(out)) == 0\n"
+            "    print(out.value)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for perturb in ("0", "165", "77"):
+        env = dict(os.environ, MALLOC_PERTURB_=perturb, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        seen.add(r.stdout)
+    assert len(seen) == 1
+
+
 def test_bvh_builder_names_the_first_triangle_with_a_non_finite_vertex():
     """NaN and infinite vertices are refused by the builder (a triangle the linear scan can never hit has no box to
     put in a tree), and the message names the lowest such triangle whichever host thread met it."""
