@@ -284,7 +284,8 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
     env.barrier()
     ms, kernel_ms = env.max_over_ranks(ev0.elapsed_time(ev1) / steps, ctx.last_kernel_ms())
     # region (b), host buffers: one step
-    host = np.empty((H, W, 3), np.float64)
+    host_pinned = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()   # as the headline's region (b): the frame lands in pinned memory
+    host = host_pinned.numpy()
     env.barrier()
     t0 = time.perf_counter()
     flat_b = sd.flatten()                    # Scene::from_data's flattening belongs to the region
@@ -311,7 +312,7 @@ def bench_render_config(env: Env, name: str, sd, root: int, seed: int, steps: in
     out = {"workload": name, "image": [W, H], "spp": root * root, "shapes": int(flat.n_shapes), "n_gpus": env.world,
            "value": n_samples / e2e_s / 1e6, "unit": "Msamples/s",
            "value_region": "host-buffer C-ABI: flatten + flux_set_scene" + (" (BVH build)" if bvh else "") +
-                           " + flux_generate_samples + render + frame to host memory",
+                           " + flux_generate_samples + render + frame to pinned host memory",
            "value_resident": n_samples / (ms * 1e-3) / 1e6, "ms_per_step": ms, "kernel_ms": kernel_ms,
            "h2d_bytes_per_step": int(flat.n_shapes) * 112, "d2h_bytes_per_step": H * W * 24,
            "segments_per_sample": tot["segments"] / max(1.0, tot["samples"]),

@@ -123,6 +123,18 @@ int fail(flux_ctx *c, int code, const std::string &msg) {
     return code;
 }
 
+// No exception crosses the C ABI (std::bad_alloc from a host vector or a message string is the one that can arise): the
+// entry points that allocate are function-try-blocks ending here.
+int caught(flux_ctx *c, const char *where) noexcept {
+    try {
+        const std::string msg = std::string(where) + ": out of host memory (or another host-side exception)";
+        if (c) c->err = msg;
+        else g_create_error = msg;
+    } catch (...) {
+    }
+    return FLUX_ERR_INVALID;
+}
+
 #define CK(call)                                                                                       \
     do {                                                                                               \
         cudaError_t e__ = (call);                                                                      \
@@ -264,7 +276,7 @@ int flux_ctx_destroy(flux_ctx *ctx) {
 
 static int build_glossy_table(flux_ctx *ctx);
 
-int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_config *cfg) {
+int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_config *cfg) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!s || !cfg) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: null scene or config");
     if (s->image_width == 0 || s->image_height == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_set_scene: empty image");
@@ -504,6 +516,8 @@ int flux_set_scene(flux_ctx *ctx, const flux_scene_flat *s, const flux_job_confi
     ctx->ss.ghemi = nullptr;
     ctx->ss.gk = 0;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_set_scene");
 }
 
 // (Re)build the glossy lobe table for the current scene and sample sets.  Skipped (kernels fall back to
@@ -544,7 +558,7 @@ static int alloc_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint3
 }
 
 int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t num_sets, const double *pixel_xy,
-                     const double *disc_xy, const double *hemi_xyz) {
+                     const double *disc_xy, const double *hemi_xyz) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_set_samples: call flux_set_scene first");
     if (root == 0 || num_sets == 0 || !pixel_xy || !disc_xy || (max_depth && !hemi_xyz))
@@ -576,9 +590,11 @@ int flux_set_samples(flux_ctx *ctx, uint32_t root, uint32_t max_depth, uint32_t 
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_samples = true;
     return build_glossy_table(ctx);
+} catch (...) {
+    return caught(ctx, "flux_set_samples");
 }
 
-int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
+int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_generate_samples: call flux_set_scene first");
     if (num_sets == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_generate_samples: num_sets must be >= 1");
@@ -607,6 +623,8 @@ int flux_generate_samples(flux_ctx *ctx, uint64_t seed, uint32_t num_sets) {
     ctx->have_index = true;
     ctx->idx_W = ctx->cam.W; ctx->idx_H = ctx->cam.H; ctx->idx_sets = num_sets;
     return build_glossy_table(ctx);
+} catch (...) {
+    return caught(ctx, "flux_generate_samples");
 }
 
 int flux_get_samples(flux_ctx *ctx, double *pixel_xy, double *disc_xy, double *hemi_xyz) {
@@ -632,7 +650,7 @@ int flux_get_set_index(flux_ctx *ctx, uint32_t *idx) {
     return FLUX_OK;
 }
 
-int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx) {
+int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_set_set_index: call flux_set_scene first");
     if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "flux_set_set_index: set or generate samples first");
@@ -648,6 +666,8 @@ int flux_set_set_index(flux_ctx *ctx, const uint32_t *idx) {
     ctx->have_index = true;
     ctx->idx_W = ctx->cam.W; ctx->idx_H = ctx->cam.H; ctx->idx_sets = ctx->ss.num_sets;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_set_set_index");
 }
 
 int flux_shard_rows(uint32_t image_height, uint32_t tile_rows, uint32_t rank, uint32_t world, uint32_t *rows,
@@ -735,14 +755,16 @@ static int render_common(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     return FLUX_OK;
 }
 
-int flux_render_row_list_device(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *d_out_rgb, void *cuda_stream) {
+int flux_render_row_list_device(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *d_out_rgb, void *cuda_stream) try {
     if (!ctx) return FLUX_ERR_INVALID;
     DeviceGuard g(ctx->device);
     // rows are copied from pageable host memory: the copy is staged before return
     return render_common(ctx, rows, n_rows, d_out_rgb, (cudaStream_t)cuda_stream, true);
+} catch (...) {
+    return caught(ctx, "flux_render_row_list_device");
 }
 
-int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *out_rgb) {
+int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, double *out_rgb) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (n_rows && !out_rgb) return fail(ctx, FLUX_ERR_INVALID, "render: null output");
     DeviceGuard g(ctx->device);
@@ -754,6 +776,8 @@ int flux_render_row_list(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, d
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_rows) CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_render_row_list");
 }
 
 // ---- multi-GPU frame assembly over peer memory (include/fluxb200.h) ----------------------------------------------
@@ -768,7 +792,7 @@ struct flux_frame {
 
 extern "C" {
 
-int flux_frame_create(flux_ctx *ctx, uint32_t W, uint32_t H, flux_frame **out) {
+int flux_frame_create(flux_ctx *ctx, uint32_t W, uint32_t H, flux_frame **out) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!out || W == 0 || H == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_create: bad arguments");
     *out = nullptr;
@@ -788,6 +812,8 @@ int flux_frame_create(flux_ctx *ctx, uint32_t W, uint32_t H, flux_frame **out) {
     }
     *out = f;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_frame_create");
 }
 
 int flux_frame_export(flux_frame *f, unsigned char *handle) {
@@ -803,7 +829,7 @@ int flux_frame_export(flux_frame *f, unsigned char *handle) {
     return FLUX_OK;
 }
 
-int flux_frame_open_ipc(flux_ctx *ctx, const unsigned char *handle, uint32_t W, uint32_t H, flux_frame **out) {
+int flux_frame_open_ipc(flux_ctx *ctx, const unsigned char *handle, uint32_t W, uint32_t H, flux_frame **out) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!out || !handle || W == 0 || H == 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_ipc: bad arguments");
     *out = nullptr;
@@ -820,9 +846,11 @@ int flux_frame_open_ipc(flux_ctx *ctx, const unsigned char *handle, uint32_t W, 
     f->device = ctx->device; f->p = (double *)p; f->W = W; f->H = H; f->kind = 1;
     *out = f;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_frame_open_ipc");
 }
 
-int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner, flux_frame **out) {
+int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner, flux_frame **out) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!out || !owner || owner->kind != 0) return fail(ctx, FLUX_ERR_INVALID, "flux_frame_open_peer: bad arguments");
     *out = nullptr;
@@ -843,9 +871,11 @@ int flux_frame_open_peer(flux_ctx *ctx, flux_frame *owner, flux_frame **out) {
     f->device = ctx->device; f->p = owner->p; f->W = owner->W; f->H = owner->H; f->kind = 2;
     *out = f;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_frame_open_peer");
 }
 
-int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, flux_frame *frame, void *cuda_stream) {
+int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows, flux_frame *frame, void *cuda_stream) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!frame) return fail(ctx, FLUX_ERR_INVALID, "render: null frame");
     if (ctx->have_scene && (frame->W != ctx->cam.W || frame->H != ctx->cam.H))
@@ -853,6 +883,8 @@ int flux_render_row_list_into_frame(flux_ctx *ctx, const uint32_t *rows, uint32_
     if (frame->device != ctx->device) return fail(ctx, FLUX_ERR_INVALID, "render: the frame was opened for another device");
     DeviceGuard g(ctx->device);
     return render_common(ctx, rows, n_rows, frame->p, (cudaStream_t)cuda_stream, true, true);
+} catch (...) {
+    return caught(ctx, "flux_render_row_list_into_frame");
 }
 
 int flux_ctx_sync(flux_ctx *ctx) {
@@ -888,7 +920,7 @@ int flux_frame_close(flux_frame *f) {
     return FLUX_OK;
 }
 
-int flux_progressive_begin(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows) {
+int flux_progressive_begin(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows) try {
     if (!ctx) return FLUX_ERR_INVALID;
     ctx->prog_active = false;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "progressive: scene not set");
@@ -907,9 +939,11 @@ int flux_progressive_begin(flux_ctx *ctx, const uint32_t *rows, uint32_t n_rows)
     ctx->prog_done = 0;
     ctx->prog_active = true;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_progressive_begin");
 }
 
-int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_end, double *out_rgb) {
+int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_end, double *out_rgb) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->prog_active) return fail(ctx, FLUX_ERR_STATE, "progressive: flux_progressive_begin not called (or the scene changed since)");
     if (!ctx->have_samples) return fail(ctx, FLUX_ERR_STATE, "render: sample sets not set");
@@ -955,34 +989,41 @@ int flux_progressive_pass(flux_ctx *ctx, uint32_t sample_begin, uint32_t sample_
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_progressive_pass");
 }
 
 static int row_range(flux_ctx *ctx, uint32_t a, uint32_t b, std::vector<uint32_t> &rows) {
+    if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "render: scene not set");   // (before a row list of any length is made)
     if (b < a) return fail(ctx, FLUX_ERR_INVALID, "render: row_end < row_start");
-    if (ctx->have_scene && b >= ctx->cam.H) return fail(ctx, FLUX_ERR_INVALID, "render: row out of range");
+    if (b >= ctx->cam.H) return fail(ctx, FLUX_ERR_INVALID, "render: row out of range");
     rows.resize((size_t)b - a + 1);
     for (uint32_t r = a; r <= b; r++) rows[r - a] = r;
     return FLUX_OK;
 }
 
-int flux_render_rows(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *out_rgb) {
+int flux_render_rows(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *out_rgb) try {
     if (!ctx) return FLUX_ERR_INVALID;
     std::vector<uint32_t> rows;
     int rc = row_range(ctx, row_start, row_end_inclusive, rows);
     if (rc) return rc;
     return flux_render_row_list(ctx, rows.data(), (uint32_t)rows.size(), out_rgb);
+} catch (...) {
+    return caught(ctx, "flux_render_rows");
 }
 
-int flux_render_rows_device(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *d_out_rgb, void *cuda_stream) {
+int flux_render_rows_device(flux_ctx *ctx, uint32_t row_start, uint32_t row_end_inclusive, double *d_out_rgb, void *cuda_stream) try {
     if (!ctx) return FLUX_ERR_INVALID;
     std::vector<uint32_t> rows;
     int rc = row_range(ctx, row_start, row_end_inclusive, rows);
     if (rc) return rc;
     return flux_render_row_list_device(ctx, rows.data(), (uint32_t)rows.size(), d_out_rgb, cuda_stream);
+} catch (...) {
+    return caught(ctx, "flux_render_rows_device");
 }
 
 int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const double *d_d, int32_t *d_hit, double *d_t,
-                           void *cuda_stream) {
+                           void *cuda_stream) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_trace_rays: scene not set");
     if (n == 0) return FLUX_OK;
@@ -999,13 +1040,15 @@ int flux_trace_rays_device(flux_ctx *ctx, uint64_t n, const double *d_o, const d
     CK(cudaGetLastError());
     CK(cudaStreamWaitEvent(us, ctx->ev1, 0));
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_trace_rays_device");
 }
 
 // Host-buffer form: the batch goes through the device in pieces of TRACE_PIECE rays on three streams — upload of
 // piece k+1, traversal of piece k and download of piece k-1 overlap (the PCIe link, 48 bytes in and 12 out per ray, is
 // the bound of this entry point: the kernel alone runs at several times its rate).  Pinned caller memory makes the
 // copies truly asynchronous; pageable memory works, staged by the driver.
-int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d, int32_t *hit, double *t) {
+int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d, int32_t *hit, double *t) try {
     if (!ctx) return FLUX_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, FLUX_ERR_STATE, "flux_trace_rays: scene not set");
     if (n == 0) return FLUX_OK;
@@ -1068,6 +1111,8 @@ int flux_trace_rays(flux_ctx *ctx, uint64_t n, const double *o, const double *d,
     ctx->last_ms = total_ms;   // the kernels alone
     ctx->ms_pending = false;
     return FLUX_OK;
+} catch (...) {
+    return caught(ctx, "flux_trace_rays");
 }
 
 int flux_enable_counters(flux_ctx *ctx, int enable) {
@@ -1121,7 +1166,7 @@ int flux_set_accel_mode(flux_ctx *ctx, int mode) {
     return FLUX_OK;
 }
 
-int flux_bvh_hash(const flux_scene_flat *s, uint64_t *hash) {
+int flux_bvh_hash(const flux_scene_flat *s, uint64_t *hash) try {
     if (!s || !hash) return FLUX_ERR_INVALID;
     const uint32_t ns = s->n_spheres, nt = s->n_triangles;
     if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
@@ -1154,9 +1199,11 @@ int flux_bvh_hash(const flux_scene_flat *s, uint64_t *hash) {
     mix(&bb.extent, sizeof bb.extent);
     *hash = h;
     return FLUX_OK;
+} catch (...) {
+    return caught(nullptr, "flux_bvh_hash");
 }
 
-int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
+int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) try {
     if (!s || !out) return FLUX_ERR_INVALID;
     const uint32_t ns = s->n_spheres, nt = s->n_triangles;
     if ((ns && (!s->sphere_center || !s->sphere_radius || !s->sphere_invert || !s->sphere_shape_id || !s->sphere_material)) ||
@@ -1232,6 +1279,8 @@ int flux_bvh_describe(const flux_scene_flat *s, uint64_t out[8]) {
     out[4] = bb.prims.size(); out[5] = violations; out[6] = miscount;
     out[7] = ((uint64_t)ns + nt > FLUX_LINEAR_LIMIT) ? 1 : 0;
     return FLUX_OK;
+} catch (...) {
+    return caught(nullptr, "flux_bvh_describe");
 }
 
 int flux_set_kernel_mode(flux_ctx *ctx, int mode) {
