@@ -566,7 +566,16 @@ std::unique_ptr<FlatScene> SceneData::flatten() const {
         } else {
             const MeshData &m = std::get<MeshData>(sh);
             const uint32_t mat = mat_id(m.material);
-            for (const auto &fc : m.faces) push_tri(m.vertices[fc[0]], m.vertices[fc[1]], m.vertices[fc[2]], mat);
+            const size_t nf = m.faces.size(), nv = m.vertices.size();
+            for (std::vector<double> *v : {&f.tri_v0, &f.tri_v1, &f.tri_v2}) v->reserve(v->size() + 3 * nf);
+            f.tri_shape_id.reserve(f.tri_shape_id.size() + nf);
+            f.tri_material.reserve(f.tri_material.size() + nf);
+            for (const auto &fc : m.faces) {
+                // the YAML reader has checked this; a MeshData built in code has not
+                for (int k = 0; k < 3; k++)
+                    if (fc[k] < 0 || (size_t)fc[k] >= nv) throw Error("Mesh.faces: vertex index out of range");
+                push_tri(m.vertices[fc[0]], m.vertices[fc[1]], m.vertices[fc[2]], mat);
+            }
         }
     }
     f.n_shapes = shape_id;
