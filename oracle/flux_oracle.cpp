@@ -10,6 +10,9 @@
 // restatement is pinned only by (i) hand-derived known-answer vectors in
 // tests/test_oracle_known_answers.py and (ii) statistically, by the RMSE of a
 // converged demo2 render against the reference's own demo.png.
+// (iii) oracle/second_opinion.py, a second restatement written from the Rust
+// sources independently of this one, agrees with it bit for bit on whole
+// renders (tests/test_second_opinion.py): no transcription slip, still no pin.
 //
 // Third-party arithmetic that is not under /root/reference and is restated
 // from its published behaviour: nalgebra 0.16.10 (Cargo.lock) Vector3/Point3
