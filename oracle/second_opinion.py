@@ -187,6 +187,31 @@ def to_unit_hemi(px, py, e):
     return normalize((sin_theta * cos_phi, sin_theta * sin_phi, cos_theta))
 
 
+def to_poisson_disc(px, py):
+    """samplers/src/lib.rs:144-182 (Shirley's concentric map, with the reference's `spy != 0.0` guard)"""
+    spx = 2.0 * px - 1.0
+    spy = 2.0 * py - 1.0
+    if spx > -spy:
+        if spx > spy:
+            r = spx
+            phi = _div(spy, spx)
+        else:
+            r = spy
+            phi = 2.0 - _div(spx, spy)
+    else:
+        if spx < spy:
+            r = -spx
+            phi = 4.0 + _div(spy, spx)
+        else:
+            r = -spy
+            if spy != 0.0:
+                phi = 6.0 - _div(spx, spy)
+            else:
+                phi = 0.0
+    phi *= math.pi / 4.0
+    return (r * math.cos(phi), r * math.sin(phi))
+
+
 class Scene:
     """Scene::from_data, scene.rs:128-154: the shapes in the order of the scene file."""
 

@@ -76,3 +76,19 @@ def test_closest_hit_ids_and_distances_bit_for_bit():
     hit = ids >= 0
     assert hit.sum() > 500
     assert np.array_equal(t[hit].view(np.uint64), t2[hit].view(np.uint64))
+
+
+def test_sample_maps_bit_for_bit():
+    """The two maps between sample domains — unit square to unit disc (Shirley, samplers/src/lib.rs:144-182) and to the
+    hemisphere with exponent e (lib.rs:133-142) — on random points, the branch boundaries of the disc map and the
+    exponents the scenes use."""
+    rng = np.random.default_rng(5)
+    pts = rng.random((2000, 2))
+    pts[:8] = [(0.5, 0.5), (0.0, 0.0), (1.0, 1.0), (0.25, 0.75), (0.75, 0.25), (0.5, 0.0), (0.0, 0.5), (0.5, 1.0)]
+    for x, y in pts:
+        a, b = O.to_poisson_disc(float(x), float(y)), np.array(S2.to_poisson_disc(float(x), float(y)))
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (x, y, a, b)
+    for e in (0.0, 1.0, 10.0, 50.0, 5000.0, 100000.0):
+        for x, y in pts[:400]:
+            a, b = O.to_unit_hemi(float(x), float(y), e), np.array(S2.to_unit_hemi(float(x), float(y), e))
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (x, y, e, a, b)
