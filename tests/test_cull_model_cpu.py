@@ -199,3 +199,134 @@ def test_primary_mask_never_drops_a_box_a_camera_ray_of_the_pixel_passes(seed):
             hit = exact_bbox_hit(np.repeat(c[j:j + 1], n_r, 0), np.repeat(r[j:j + 1], n_r), orig, dirs)
             assert not hit.any(), f"sphere {j} left out of the mask of pixel ({col}, {row}) is hit by {hit.sum()} camera rays"
     assert total_excluded > 1000      # the mask does something on these scenes
+
+
+# ---- the BVH's FP32 node test (flux_bvh.cuh: BvhTraversal::begin + BVH_CHILD) -------------------------------------------
+def _dot(a, b):
+    return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+
+
+def exact_sphere_t(c, r, o, d):
+    """Sphere::hit distance (shapes.rs:171-217) or NaN, vectorised."""
+    with np.errstate(all="ignore"):
+        ok = exact_bbox_hit(c, r, o, d)
+        temp = o - c
+        a = _dot(d, d)
+        b = 2.0 * _dot(temp, d)
+        cc = _dot(temp, temp) - r * r
+        disc = b * b - 4.0 * a * cc
+        e = np.sqrt(np.where(disc < 0.0, np.nan, disc))
+        t1, t2 = (-b - e) / (2.0 * a), (-b + e) / (2.0 * a)
+        t = np.where(t1 > T_MIN, t1, np.where(t2 > T_MIN, t2, np.nan))
+        return np.where(ok, t, np.nan)
+
+
+def exact_tri_t(v0, e1, e2, o, d):
+    """tri_t (flux_intersect.cuh / oracle tri_hit: the extension's definition) or NaN."""
+    with np.errstate(all="ignore"):
+        p = np.cross(d, e2)
+        det = _dot(e1, p)
+        s = o - v0
+        inv = 1.0 / det
+        u = _dot(s, p) * inv
+        q = np.cross(s, e1)
+        v = _dot(d, q) * inv
+        t = _dot(e2, q) * inv
+        ok = (det != 0.0) & (u >= 0.0) & (u <= 1.0) & (v >= 0.0) & (u + v <= 1.0) & (t > T_MIN)
+        return np.where(ok, t, np.nan)
+
+
+def round_out(lo, hi):
+    """Builder::set_child: f64 box to f32, outward."""
+    flo, fhi = lo.astype(F32), hi.astype(F32)
+    flo = np.where(flo.astype(np.float64) > lo, np.nextafter(flo, F32(-np.inf)), flo)
+    fhi = np.where(fhi.astype(np.float64) < hi, np.nextafter(fhi, F32(np.inf)), fhi)
+    return flo, fhi
+
+
+def node_test_f32(flo, fhi, o, d, ext, t_best):
+    """True where the traversal would SKIP the child box [flo, fhi] for a ray whose best hit so far is t_best."""
+    with np.errstate(all="ignore"):
+        df, of = d.astype(F32), o.astype(F32)
+        a = (F32(1.0) / df).astype(F32)
+        a = np.where(np.abs(a) < F32(1e30), a, np.copysign(F32(1e30), df))
+        noa = (-(of * a)).astype(F32)
+        extf = np.nextafter(ext.astype(F32), F32(np.inf))[:, None]
+        E = (np.abs(a) * (extf + np.abs(of)) * F32(1.01 * 9.5367431640625e-07)).astype(F32)
+        sane = (df == df) & (np.abs(noa) < F32(1e37)) & (E < F32(1e37))
+        pos = ~np.signbit(a)
+        ia = np.where(sane, a, F32(0.0))
+        nlo = np.where(sane, (noa - E).astype(F32), F32(-np.inf))
+        nhi = np.where(sane, (noa + E).astype(F32), F32(np.inf))
+        near, far = np.where(pos, flo, fhi), np.where(pos, fhi, flo)
+        sn, sf = fma32(near, ia, nlo), fma32(far, ia, nhi)
+        tn = np.fmax(np.fmax(sn[:, 0], sn[:, 1]), sn[:, 2])
+        tf = np.fmin(np.fmin(sf[:, 0], sf[:, 1]), sf[:, 2])
+        inv = 1.0 / d
+        tscale = ext * np.minimum(np.abs(inv[:, 0]), np.minimum(np.abs(inv[:, 1]), np.abs(inv[:, 2])))
+        t_prune = t_best + 1e-9 * (np.abs(t_best) + tscale)
+        tp32 = t_prune.astype(F32)
+        tp32 = np.where(tp32.astype(np.float64) < t_prune, np.nextafter(tp32, F32(np.inf)), tp32)   # __double2float_ru
+        return (tn > tf) | (tf < F32(0.000499)) | (tn > tp32)
+
+
+@pytest.mark.parametrize("scale", [1.0, 50.0, 1e3])
+def test_bvh_node_test_never_skips_a_box_whose_primitive_yields_the_hit(scale):
+    """A node may be skipped only if nothing below it can give a candidate at or before the best hit.  Hardest case: the
+    child box is the primitive's own box (padded by 1e-7 of the scene extent and rounded outward, as the builder makes a
+    leaf's box) and the best hit so far is this very primitive's distance (a tie the lower shape id must still win)."""
+    rng = np.random.default_rng(int(scale) + 17)
+    n = 300_000
+    # spheres, rays through random points of the ball — many grazing — from near and far, some inside
+    c = rng.uniform(-scale, scale, (n, 3))
+    r = 10.0 ** rng.uniform(-3, 0, n) * scale * 0.1
+    u = rng.normal(0, 1, (n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    rad = np.where(rng.random(n) < 0.5, 1.0 - 10.0 ** rng.uniform(-12, -1, n), rng.random(n) ** (1 / 3))
+    q = c + u * (r * rad)[:, None]
+    o = q + rng.normal(0, 1, (n, 3)) * rng.choice([0.01, 1.0, 30.0], (n, 1)) * scale
+    d = q - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    flat = rng.random(n) < 0.15                    # nearly axis-parallel: huge reciprocals on the other axes
+    d[flat] *= np.array([1.0, 1e-9, 1e-7])
+    d[flat] /= np.linalg.norm(d[flat], axis=1, keepdims=True)
+    zero = rng.random(n) < 0.05
+    d[zero, 2] = 0.0
+    t = exact_sphere_t(c, r, o, d)
+    ext = (np.abs(c) + r[:, None]).max(axis=1) * rng.choice([1.0, 1.0, 4.0], n)     # the scene holds at least this sphere
+    pad = 1e-7 * ext
+    flo, fhi = round_out(c - r[:, None] - pad[:, None], c + r[:, None] + pad[:, None])
+    hit = ~np.isnan(t)
+    assert hit.sum() > n // 3
+    skip = node_test_f32(flo, fhi, o, d, ext, np.where(hit, t, np.inf))
+    assert not (skip & hit).any(), f"{(skip & hit).sum()} sphere hits lost behind their own node box"
+    # ... and the test is worth having: rays that miss the box by a clear margin are skipped
+    far_off = c + u * (r * 4.0)[:, None] + 3.0 * r[:, None]
+    d2 = far_off - o
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    miss = ~exact_bbox_hit(c, r * 1.5, o, d2)
+    assert node_test_f32(flo, fhi, o, d2, ext, np.full(n, np.inf))[miss].mean() > 0.95
+
+    # triangles, rays through random points of the face — many on its edges
+    v0 = rng.uniform(-scale, scale, (n, 3))
+    e1, e2 = rng.normal(0, 0.05 * scale, (n, 3)), rng.normal(0, 0.05 * scale, (n, 3))
+    e1[: n // 10, 1] = 0.0
+    e2[: n // 10, 1] = 0.0                                   # axis-aligned faces: a box of zero thickness
+    b1, b2 = rng.random(n), rng.random(n)
+    fold = b1 + b2 > 1.0
+    b1, b2 = np.where(fold, 1.0 - b1, b1), np.where(fold, 1.0 - b2, b2)
+    b2 = np.where(rng.random(n) < 0.3, 10.0 ** rng.uniform(-14, -6, n), b2)           # along an edge
+    q = v0 + e1 * b1[:, None] + e2 * b2[:, None]
+    o = q + rng.normal(0, 1, (n, 3)) * rng.choice([0.01, 1.0, 30.0], (n, 1)) * scale
+    d = q - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    t = exact_tri_t(v0, e1, e2, o, d)
+    v1, v2 = v0 + e1, v0 + e2
+    lo, hi = np.minimum(np.minimum(v0, v1), v2), np.maximum(np.maximum(v0, v1), v2)
+    ext = np.abs(np.concatenate([lo, hi], axis=1)).max(axis=1) * rng.choice([1.0, 1.0, 4.0], n)
+    pad = 1e-7 * ext
+    flo, fhi = round_out(lo - pad[:, None], hi + pad[:, None])
+    hit = ~np.isnan(t)
+    assert hit.sum() > n // 3
+    skip = node_test_f32(flo, fhi, o, d, ext, np.where(hit, t, np.inf))
+    assert not (skip & hit).any(), f"{(skip & hit).sum()} triangle hits lost behind their own node box"
