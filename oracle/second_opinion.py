@@ -393,3 +393,78 @@ def trace(sd: SceneData, origins, dirs):
         h = scene.hit(tuple(float(x) for x in o), tuple(float(x) for x in d), 1)
         res.append((-1, math.inf) if h is None else (h.shape, h.distance))
     return res
+
+
+# ---- sample-set structure (samplers/src/lib.rs:46-126), on this repository's counter-based random source -------------------------
+# The reference draws from one unseeded IsaacRng in sequence; this repository replaces the SOURCE of the random numbers
+# by keyed counters (explicit, seeded sample sets) and keeps the STRUCTURE.  What is restated a second time
+# here is that structure — the base grid, shuffle_y / shuffle_x and the transposes between them, written as the reference
+# writes them instead of the closed form `out[i*root+j] = {base[pix_j(i)][j].x, base[i][piy_i(j)].y}` the C++ uses — fed
+# from the same keyed source (mix64 / stream_key / rnd below restate oracle/flux_oracle.cpp's, not the reference's).
+_M = (1 << 64) - 1
+P_JITTER, P_PERM_Y, P_PERM_X = 0, 1, 2
+
+
+def _mix64(z):
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M
+    return z ^ (z >> 31)
+
+
+def _stream_key(seed, a, b, c, d):
+    k = _mix64((seed + 0x9E3779B97F4A7C15) & _M)
+    for x in (a, b, c, d):
+        k = _mix64((k + x) & _M)
+    return k
+
+
+def _rnd(key, ctr):
+    return _mix64((key + (ctr + 1) * 0x9E3779B97F4A7C15) & _M)
+
+
+def _u01(x):
+    return float(x >> 11) * (1.0 / 9007199254740992.0)
+
+
+def _shuffled_identity(n, key):
+    """Rng::shuffle (rand 0.5.5) of 0..n: for i = n-1 down to 1: swap(i, gen_range(0, i+1))"""
+    v = list(range(n))
+    for i in range(n - 1, 0, -1):
+        j = (_rnd(key, i) * (i + 1)) >> 64
+        v[i], v[j] = v[j], v[i]
+    return v
+
+
+def _transpose(m):
+    return [list(col) for col in zip(*m)]
+
+
+def _shuffle_y(idxs, vals):     # lib.rs:92-108
+    return [(sample[0], vals[idx][1]) for idx, sample in zip(idxs, vals)]
+
+
+def _shuffle_x(idxs, vals):     # lib.rs:110-126
+    return [(vals[idx][0], sample[1]) for idx, sample in zip(idxs, vals)]
+
+
+def mj_grid(seed, root, set_, grid, correlated):
+    """grid_multi_jittered (lib.rs:64-73) / grid_correlated_multi_jittered (lib.rs:75-90): root*root (x, y) tuples."""
+    r2 = float(root * root)
+    r_float = float(root)
+    kj = _stream_key(seed, set_, grid, P_JITTER, 0)
+    rng_range = [(float(v), float(root - 1 - v)) for v in range(root)]
+    samples = []                # grid_multi_jittered_base, lib.rs:46-62
+    for i, (big_row, little_col) in enumerate(rng_range):
+        row = []
+        for j, (big_col, little_row) in enumerate(rng_range):
+            c = 2 * (i * root + j)
+            a, b = _u01(_rnd(kj, c)), _u01(_rnd(kj, c + 1))
+            row.append(((big_row / r_float) + (little_row + a) / r2, (big_col / r_float) + (little_col + b) / r2))
+        samples.append(row)
+
+    def idx(kind, line):
+        return _shuffled_identity(root, _stream_key(seed, set_, grid, kind, 0 if correlated else line))
+
+    y_shuffled = [_shuffle_y(idx(P_PERM_Y, line), vec) for line, vec in enumerate(samples)]
+    x_shuffled = _transpose([_shuffle_x(idx(P_PERM_X, line), v) for line, v in enumerate(_transpose(y_shuffled))])
+    return [p for row in x_shuffled for p in row]     # concat_vec

@@ -92,3 +92,15 @@ def test_sample_maps_bit_for_bit():
         for x, y in pts[:400]:
             a, b = O.to_unit_hemi(float(x), float(y), e), np.array(S2.to_unit_hemi(float(x), float(y), e))
             assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (x, y, e, a, b)
+
+
+@pytest.mark.parametrize("correlated", [False, True])
+def test_multi_jittered_structure_bit_for_bit(correlated):
+    """grid_multi_jittered / grid_correlated_multi_jittered (samplers/src/lib.rs:46-126) written with the reference's
+    shuffles and transposes, against the C++ oracle's closed form, on the same keyed random source: which base point's x
+    and which base point's y end up in cell (i, j)."""
+    for root in (1, 2, 3, 5, 8, 13):
+        for set_, grid in ((0, 0), (3, 1), (7, 4)):
+            a = O.mj_grid(9, root, set_, grid, correlated)
+            b = np.array(S2.mj_grid(9, root, set_, grid, correlated), np.float64).reshape(-1, 2)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (root, set_, grid)
