@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(WAVE2_S, WAVE2_MIN_BLOCKS) render_wave2_kernel
                 const uint32_t sm = w.meta[sl];
                 const uint32_t depth = meta_depth(sm), top = meta_top(sm), mi = meta_mat(sm);
 #if WAVE2_ORDER == 0
-                const uint32_t a_spec = n_term, a_gloss = n_term + n_spec, a_matte = a_gloss + n_gloss;   // block starts
+                const uint32_t a_gloss = n_term + n_spec, a_matte = a_gloss + n_gloss;   // block starts (specular: n_term)
                 const bool is_matte = tid >= a_matte, is_spec = tid < a_gloss;
 #else
                 const uint32_t a_matte = n_term, a_spec = n_term + n_matte, a_gloss = a_spec + n_spec;
