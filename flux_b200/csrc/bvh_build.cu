@@ -322,7 +322,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
     }
     const size_t n_items = tri_base + nt;
     std::vector<uint32_t> first_bad(1, 0xFFFFFFFFu);
-    std::mutex bad_mu;
+    std::mutex merge_mu;   // what the slices hand back: the first bad triangle, their partial bounds
     in_slices(nt, [&](uint32_t lo_i, uint32_t hi_i) {
     Box part_c, part_b;
     part_c.reset(); part_b.reset();
@@ -345,7 +345,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         for (int k = 0; k < 3; k++)   // min / max skip a NaN or not depending on where it stands: look at the vertices themselves
             finite = finite && std::isfinite(v0[k]) && std::isfinite(tri_v1[3 * (size_t)i + k]) && std::isfinite(tri_v2[3 * (size_t)i + k]);
         if (!finite) {
-            std::lock_guard<std::mutex> g(bad_mu);
+            std::lock_guard<std::mutex> g(merge_mu);
             first_bad[0] = std::min(first_bad[0], i);   // the lowest index, whichever thread saw it
         }
         part_b.grow(bx);
@@ -356,7 +356,7 @@ static bool build_bvh4_impl(const double *sph, const uint32_t *sph_meta, uint32_
         boxes[tri_base + i] = bx;
         items[tri_base + i] = it;
     }
-    std::lock_guard<std::mutex> g(bad_mu);
+    std::lock_guard<std::mutex> g(merge_mu);
     tri_cb.grow(part_c);
     tri_all.grow(part_b);
     });
