@@ -300,6 +300,11 @@ def test_bvh_node_test_never_skips_a_box_whose_primitive_yields_the_hit(scale):
     assert hit.sum() > n // 3
     skip = node_test_f32(flo, fhi, o, d, ext, np.where(hit, t, np.inf))
     assert not (skip & hit).any(), f"{(skip & hit).sum()} sphere hits lost behind their own node box"
+    # ancestors: any box that contains this one (rounding is monotone, so the slabs only widen)
+    grow = (10.0 ** rng.uniform(-9, 1, (n, 3)) * r[:, None]).astype(F32)
+    skip = node_test_f32(flo - grow * rng.integers(0, 2, (n, 3)).astype(F32), fhi + grow * rng.integers(0, 2, (n, 3)).astype(F32),
+                         o, d, ext, np.where(hit, t, np.inf))
+    assert not (skip & hit).any(), f"{(skip & hit).sum()} sphere hits lost behind an ancestor's box"
     # ... and the test is worth having: rays that miss the box by a clear margin are skipped
     far_off = c + u * (r * 4.0)[:, None] + 3.0 * r[:, None]
     d2 = far_off - o
